@@ -1,0 +1,179 @@
+/*
+ * qpg.h -- C ABI of libqpg_sm100.so: the B200 (sm_100a) implementation of
+ * QPGesture's inference hot path.
+ *
+ * The reference (YoungSeng/QPGesture @ 7dd5daa) is pure Python and has no FFI;
+ * its boundary for this path is the Python call surface of
+ *   codebook/Speech2GestureMatching/GestureKNN.py  (CodeKNN, wavvq_distances)
+ *   codebook/models/{vqvae,bottleneck,encdec,resnet}.py (VQVAE encode/decode)
+ * Each entry point below names the reference lines it replaces.  The Python
+ * shims in qpgesture_b200/ keep those names/arguments and call this library
+ * through ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
+ *
+ * Conventions
+ *  - every pointer is a caller-owned DEVICE pointer unless the name ends in
+ *    _host; nothing is allocated or freed inside the library except through
+ *    the explicit qpg_*_create/destroy pairs; no torch types, no argv/env reads
+ *  - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *    all work is enqueued on it and NOT synchronised
+ *  - return value: 0 = ok, negative = QPG_E_* ; qpg_last_error() gives a
+ *    thread-local message for the last failing call
+ *  - the distance / min-by-code tables use qpg_pair_t {double d; int64 id}:
+ *    d is the best distance of the bin (1e3 when the bin is empty, as
+ *    GestureKNN.py:668,709), id the smallest global window id attaining it
+ *    (-1 when empty) -- i.e. the result of the reference's row-major
+ *    strict-< scan (GestureKNN.py:686-689, :717-720)
+ */
+#ifndef QPG_H_
+#define QPG_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QPG_OK 0
+#define QPG_E_BADARG (-1)
+#define QPG_E_CUDA (-2)
+#define QPG_E_UNSUPPORTED (-3)
+
+#define QPG_CODEBOOK_SIZE 512 /* constant.py:56 */
+#define QPG_ROWS_PER_GROUP 8  /* packed database: rows per tile group   */
+#define QPG_CHUNK 128         /* packed database: floats per tile chunk */
+#define QPG_LEV_TOKENS 11     /* GestureKNN.py:58-60: 6 past + 5 future taps */
+#define QPG_LEV_STRIDE 12     /* tokens are stored 12 per row (48 B)    */
+
+typedef struct {
+  double d;
+  int64_t id;
+} qpg_pair_t;
+
+int qpg_version(void);
+const char* qpg_last_error(void);
+/* number of kernels this library has launched in the calling process */
+uint64_t qpg_launch_count(void);
+
+/* ---------------- packed window database ---------------------------------
+ * Row-major float32 windows [W, D] are re-laid-out once per database into
+ * [G = ceil(W/8)] [NC = ceil(D/128)] [8] [128] float32 (zero padded), so that
+ * each (group, chunk) tile is one contiguous 4 KiB block for a single TMA
+ * bulk copy, and each row's squared L2 norm is computed in float64.
+ * Replaces the materialised feature table the reference scans at
+ * GestureKNN.py:685 (wavlm_train_feat[j, k]) and :716 (context_train[j, k//8]).
+ */
+size_t qpg_packed_bytes(int64_t W, int D);
+int qpg_pack_rows_f32(const float* rows, int64_t W, int D, float* packed, double* row_sqnorm,
+                      void* stream);
+
+/* ---------------- candidate distance, cosine, fused min-by-start-code ----
+ * For each of Q query vectors q[Q, D] (float32) and every window w < W:
+ *   dist = 0.5*|| q/|q| - x_w/|x_w| ||^2      (sklearn paired cosine distance,
+ *          GestureKNN.py:685,716; evaluated as (a+b)/2 - <q,x>/(|q||x|) with
+ *          float64 accumulation of float32 data, a,b = 1 for non-zero vectors)
+ *   table[q][labels[w]] = lexicographic min of (dist, id_offset + w)
+ * `table` [Q, 512] must have been initialised with qpg_table_init (or hold a
+ * partial result to be refined, e.g. another shard of the same database).
+ * One launch handles up to 8 queries per pass over the database; Q larger than
+ * `queries_per_pass` is processed in ceil(Q/queries_per_pass) passes
+ * (0 = let the library choose from D).  Replaces CodeKNN.search_audio_cands
+ * (mode 'wavlm_feat', GestureKNN.py:666-691) and search_text_cands (:708-721).
+ */
+int qpg_table_init(qpg_pair_t* table, int64_t n_entries, void* stream);
+int qpg_cand_cosine_minbycode(const float* packed, const double* row_sqnorm, const int32_t* labels,
+                              int64_t W, int D, int64_t id_offset, const float* q, int Q,
+                              qpg_pair_t* table, int queries_per_pass, void* stream);
+
+/* ---------------- candidate distance, Levenshtein, fused min-by-code -----
+ * tokens [W, 12] uint32 (11 used: g0*320+g1 per tap, GestureKNN.py:58-60),
+ * q_tokens [Q, 12].  dist = unit-cost edit distance (Levenshtein.distance,
+ * GestureKNN.py:67), exact integers stored as double in the table.
+ * Replaces search_audio_cands mode 'wavvq_feat' + wavvq_distances 'combine'.
+ */
+int qpg_cand_lev_minbycode(const uint32_t* tokens, const int32_t* labels, int64_t W,
+                           int64_t id_offset, const uint32_t* q_tokens, int Q, qpg_pair_t* table,
+                           void* stream);
+/* plain pairwise distances (wavvq_distances(ls1, ls2, 'combine'), GestureKNN.py:44-67) */
+int qpg_lev_distance(const uint32_t* a_tokens, const uint32_t* b_tokens, int64_t n, int32_t* out,
+                     void* stream);
+
+/* ---------------- merge of per-shard tables (multi-GPU / multi-part) -----
+ * out[e] = lexicographic min over p < n_parts of parts[p][e].  Used after the
+ * all-gather of per-rank tables when database rows are sharded across GPUs.
+ */
+int qpg_table_merge(const qpg_pair_t* parts, int n_parts, int64_t n_entries, qpg_pair_t* out,
+                    void* stream);
+
+/* ---------------- rank transform ------------------------------------------
+ * ranks[q][c] = position of table[q][c].d in a stable ascending sort of the
+ * 512 distances (ties -> lower code first); the reference's
+ * np.array(dist).argsort().argsort() (GestureKNN.py:553,574) up to the order of
+ * exact ties, which NumPy leaves platform-defined.
+ */
+int qpg_rank512(const qpg_pair_t* table, int Q, int32_t* ranks, void* stream);
+
+/* ---------------- sequential tail of search_code_knn ----------------------
+ * One thread block per clip walks its n_seg*8 steps (GestureKNN.py:528-660,
+ * flag set use_phase & use_aud & use_txt):
+ *   combined_x[c] = (pos_rank[last][c] + 0.05*freq_rank[c]) + rank_x[q][c]
+ *   c_a, c_t      = argmin (ties -> lower code)
+ *   candidate     = window aud_table[q][c_a].id / txt_table[q][c_t].id
+ *   phase cosine of [prev[-5:];head[:3]] vs [prev[-3:];head[:5]] (:636,:644),
+ *   audio wins ties (:646); emit 4 codes code[j, m:m+4]; prev = window tail.
+ * Segments chain as predict_code_from_audio does (:791,:800).
+ * Shapes: pos_rank int32 [512,512]; freq_rank int32 [512]; code int32 [N,30];
+ * phase_amp float32 [N,240,16]; aud_frame/txt_frame int32 [26] = int(k/398*240)
+ * per window slot; seed_code int32 [n_clips]; seed_phase float32 [n_clips,8,16];
+ * tables/ranks [n_clips*n_seg*8, 512]; id_base = global id of window 0 of `code`.
+ * Outputs: codes int64 [n_clips, n_seg, 30]; vote int32 [n_clips, n_seg, 8]
+ * (0 = audio, 1 = text); status int32 [n_clips] (0 ok, 1 = a chosen start-code
+ * had no window: the reference raises IndexError at GestureKNN.py:631).
+ */
+int qpg_match_tail(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, const int32_t* aud_rank,
+                   const int32_t* txt_rank, const int32_t* pos_rank, const int32_t* freq_rank,
+                   const int32_t* code, int64_t n_seq, const float* phase_amp, const int32_t* aud_frame,
+                   const int32_t* txt_frame, const int32_t* seed_code, const float* seed_phase,
+                   int n_clips, int n_seg, int64_t* codes_out, int32_t* vote_out, float* phase_out,
+                   int32_t* status_out, void* stream);
+
+/* ---------------- VQ codebook L2 argmin -----------------------------------
+ * BottleneckBlock.quantise (codebook/models/bottleneck.py:120-126):
+ *   dist[m][k] = fl32( fl32(|x_m|^2 - 2*<x_m,c_k>) + |c_k|^2 ),  idx = first argmin
+ * x [M, D] float32, codebook [K, D] float32; idx_out int64 [M]; min_out float32 [M]
+ * (may be NULL).  <x,c> is accumulated in float64 and rounded once to float32.
+ */
+int qpg_vq_argmin_f32(const float* x, const float* codebook, int64_t M, int D, int K, int64_t* idx_out,
+                      float* min_out, void* stream);
+/* BottleneckBlock.dequantise (bottleneck.py:128-130): out[m,:] = codebook[idx[m],:] */
+int qpg_vq_dequantise_f32(const int64_t* idx, const float* codebook, int64_t M, int D, int K, float* out,
+                          void* stream);
+
+/* ---------------- 1-D convolution stacks of the VQ-VAE ---------------------
+ * Channels-last activations [B, T, C] float32.  One generic "tap GEMM":
+ *   out[b, t*out_stride + out_offset, co] = bias[co] + residual[...]
+ *        + sum_{tap, ci} act(in[b, t*in_stride + tap_offset[tap], ci]) * w[tap][ci][co]
+ * with act = ReLU when relu_in != 0 and zero for out-of-range input frames.
+ * Covers nn.Conv1d (encdec.py:20,24,39,113; resnet.py:33-36) and, as two
+ * output phases, nn.ConvTranspose1d k4 s2 p1 (encdec.py:45).
+ * w is [n_taps, Cin, Cout] float32 (repacked from torch's [Cout, Cin, k]).
+ * precision: 0 = float32 FFMA (parity mode), 1 = 3xTF32 tensor cores.
+ */
+typedef struct {
+  int B, T_in, T_out_total, C_in, C_out;
+  int n_taps;
+  int tap_offset[4];
+  int in_stride;   /* input frame step per output index               */
+  int out_stride;  /* output frame step (2 for transposed-conv phases) */
+  int out_offset;  /* first output frame written                      */
+  int n_out;       /* output indices t = 0..n_out-1 per batch item    */
+  int relu_in;
+  int precision;
+} qpg_conv_desc_t;
+int qpg_conv1d_taps_f32(const qpg_conv_desc_t* desc, const float* in, const float* w, const float* bias,
+                        const float* residual, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QPG_H_ */

@@ -1,0 +1,459 @@
+"""B200 drop-in for the CodeKNN half of the reference's
+codebook/Speech2GestureMatching/GestureKNN.py (:44-67, :422-845).
+
+Same public names and argument meaning -- `wavvq_distances`, `CodeKNN`
+(`search_code_knn`, `search_audio_cands`, `search_text_cands`,
+`init_code_phase`, `code_to_signature`, `code_to_freq`),
+`predict_code_from_audio`, `main_codebook`, and the CLI flags of
+GestureKNN.sh -- but the candidate scans run as CUDA kernels of
+libqpg_sm100.so over a database that stays resident in HBM, and all steps of
+all segments are evaluated in one pass (they do not depend on the sequential
+state).  There is no CPU fallback for the scans.
+
+Unlike the reference, nothing is parsed at import: `args` is filled by
+`main()` (or by `set_args`).
+"""
+from __future__ import annotations
+
+import argparse
+import os
+import random
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constant import (NUM_AUDIO_FEAT_FRAMES, SEED_VALUE, STEP_SZ, STEPS_PER_SEGMENT, WINDOWS_PER_SEQ, codebook_size,
+                       num_frames, num_frames_code)
+from .matchdb import (MatchDatabase, new_table, pad_tokens, phase_to_dense, table_to_numpy, wavvq_tokens)
+
+args = None  # module-global like the reference's (GestureKNN.py:41); set by main()/set_args()
+
+
+def build_parser() -> argparse.ArgumentParser:
+    """Flags of GestureKNN.py:25-39 (GestureKNN.sh:7-18 passes 11 of them)."""
+    p = argparse.ArgumentParser()
+    d = "/path/to/training_db_data.npz"
+    p.add_argument("-d", "--train_database", type=str, default=d)
+    p.add_argument("-c", "--train_codebook", type=str, default=d)
+    p.add_argument("-w", "--train_wavlm", type=str, default=d)
+    p.add_argument("-wvq", "--train_wavvq", type=str, default=d)
+    p.add_argument("-s", "--codebook_signature", type=str, default=d)
+    p.add_argument("-e", "--test_data", type=str, default="/path/to/test_data.npz")
+    p.add_argument("-tw", "--test_wavlm", type=str, default=d)
+    p.add_argument("-twvq", "--test_wavvq", type=str, default=d)
+    p.add_argument("-om", "--out_knn_filename", type=str, default="/path/to/knn_pred.npz")
+    p.add_argument("-ov", "--out_video_path", type=str, default="/path/to/video/")
+    p.add_argument("-k", "--desired_k", type=int, default=0)
+    p.add_argument("-f", "--fake", type=bool, default=False)
+    p.add_argument("-of", "--out_fake_knn_filename", type=str, default="/path/to/knn_pred.npz")
+    p.add_argument("--max_frames", type=int, default=0)
+    # additions (not in the reference)
+    p.add_argument("--mode", choices=("A", "B"), default="A",
+                   help="A = WavLM cosine (the literals shipped at GestureKNN.py:842-843), B = wavvq Levenshtein")
+    p.add_argument("--tail", choices=("device", "numpy"), default="device",
+                   help="where the 512-element sequential tail runs (numpy = the reference's own argsort calls)")
+    p.add_argument("--gpu", type=int, default=0)
+    return p
+
+
+def set_args(ns):
+    global args
+    args = ns
+
+
+def seed_everything(seed_value: int = SEED_VALUE):
+    """GestureKNN.py:19-22."""
+    os.environ["PYTHONHASHSEED"] = str(seed_value)
+    random.seed(seed_value)
+    np.random.seed(seed_value)
+
+
+# --------------------------------------------------------------------------
+def _lev_pairs(a_tok: np.ndarray, b_tok: np.ndarray) -> np.ndarray:
+    lib = _lib.load()
+    a = torch.from_numpy(pad_tokens(a_tok).view(np.int32)).cuda()
+    b = torch.from_numpy(pad_tokens(b_tok).view(np.int32)).cuda()
+    out = torch.empty(a.shape[0], dtype=torch.int32, device=a.device)
+    _lib.check(lib.qpg_lev_distance(_lib.ptr(a), _lib.ptr(b), a.shape[0], _lib.ptr(out), _lib.stream_ptr()),
+               "qpg_lev_distance")
+    return out.cpu().numpy()
+
+
+def wavvq_distances(ls1, ls2, mode="sum"):
+    """GestureKNN.py:44-67.  'combine': 11 tokens g0*320+g1, one edit distance.
+    'sum': the two code groups as separate strings, distances added (the
+    reference's reshape(NUM_AUDIO_FEAT_FRAMES, -1) only accepts 12 values)."""
+    ls1, ls2 = np.asarray(ls1), np.asarray(ls2)
+    if mode == "combine":
+        return int(_lev_pairs(wavvq_tokens(ls1)[None, :], wavvq_tokens(ls2)[None, :])[0])
+    if mode == "sum":
+        a = ls1.reshape(NUM_AUDIO_FEAT_FRAMES, -1).transpose()
+        b = ls2.reshape(NUM_AUDIO_FEAT_FRAMES, -1).transpose()
+        pad = np.full((2, 11 - a.shape[1]), 0xFFFFFFFF, dtype=np.int64)  # common suffix: distance unchanged
+        d = _lev_pairs(np.concatenate((a[:2].astype(np.int64), pad), 1),
+                       np.concatenate((b[:2].astype(np.int64), pad), 1))
+        return int(d[0] + d[1])
+    return None
+
+
+# --------------------------------------------------------------------------
+class CodeKNN(object):
+    """Reference constructor signature (GestureKNN.py:423-425) plus keyword-only
+    extras.  Arrays are (N, time, feat) as in the reference at this point."""
+
+    def __init__(self, mfcc_train=None, code_train=None, feat_train=None, wavlm_train=None, wavlm_train_feat=None,
+                 speech_features=None, speech_features_feat=None, wavvq_train_feat=None, phase_train=None,
+                 context_train=None, use_wavlm=False, use_wavvq=False, use_phase=False, use_txt=False, *,
+                 codebook_signature=None, train_codebook=None, device=None, database: Optional[MatchDatabase] = None,
+                 seq_range=None, process_group=None, tail="device", aud_rows=None, aud_tokens=None):
+        super().__init__()
+        self.use_phase = use_phase
+        self.phase_channels = 8
+        self.tail = tail
+        self.process_group = process_group
+        self.code_train = None if code_train is None else np.asarray(code_train)
+        self.c2s, self.c2f, self.freq_dist_cands = None, None, None
+        if database is not None:
+            self.db = database
+            self.code_train = database.code_host
+        else:
+            if not (use_wavlm or use_wavvq):
+                raise NotImplementedError("only the WavLM (use_wavlm) and wavvq (use_wavvq) matchers are built; the "
+                                          "MFCC branch of CodeKNN is not on the shipped path (GestureKNN.py:842)")
+            mode = "A" if use_wavlm else "B"
+            sig_path = codebook_signature or (args.codebook_signature if args is not None else None)
+            code_path = train_codebook or (args.train_codebook if args is not None else None)
+            if sig_path is None:
+                raise ValueError("codebook_signature path needed (reference reads args.codebook_signature, :476)")
+            signature = np.load(sig_path)["signature"] if isinstance(sig_path, str) else np.asarray(sig_path)
+            freq_code = self.code_train
+            if code_path is not None:
+                freq_code = np.load(code_path)["code"] if isinstance(code_path, str) else np.asarray(code_path)
+            n = self.code_train.shape[0]
+            ctx = np.asarray(context_train)
+            txt_rows = ctx[:, :WINDOWS_PER_SEQ, :].reshape(n * WINDOWS_PER_SEQ, -1)
+            if mode == "A" and aud_rows is None:
+                f = np.asarray(wavlm_train_feat)                      # (N, 180, 6C)
+                step = f.shape[1] // num_frames_code
+                aud_rows = f[:, 0:step * WINDOWS_PER_SEQ:step, :].reshape(n * WINDOWS_PER_SEQ, -1)
+            if mode == "B" and aud_tokens is None:
+                from .matchdb import mode_b_window_frames
+                ks, _ = mode_b_window_frames()
+                aud_tokens = wavvq_tokens(np.asarray(wavvq_train_feat)[:, ks, :]).reshape(n * WINDOWS_PER_SEQ, -1)
+            self.db = MatchDatabase(mode, self.code_train, signature, phase_to_dense(_phase_ntc(phase_train)),
+                                    txt_rows, aud_rows=aud_rows, aud_tokens=aud_tokens, freq_code=freq_code,
+                                    device=device, seq_range=seq_range)
+        self.mode = self.db.mode
+        self.step_sz = self.db.step_sz
+        self.n_db_seq = self.db.n_seq
+        self.n_db_frm = self.db.n_db_frm
+        self.code_to_signature()
+        self.code_to_freq()
+
+    # ---- reference helpers ---------------------------------------------------
+    def code_to_signature(self):
+        self.c2s = {i: self.db.signature[i] for i in range(codebook_size)}       # GestureKNN.py:475-479
+
+    def code_to_freq(self):
+        from .matchdb import code_to_freq
+        self.freq_dist_cands = None                                             # rank table lives in self.db
+        self.c2f = None
+
+    def init_code_phase(self):
+        """GestureKNN.py:462-473: two draws from NumPy's global legacy RNG."""
+        init_i = np.random.randint(0, self.n_db_seq)
+        init_j = np.random.randint(0, self.n_db_frm - int(num_frames / num_frames_code))
+        init_code = self.code_train[init_i, init_j // num_frames_code]
+        if not self.use_phase:
+            return init_code
+        return init_code, self.db.phase_amp_host[init_i, init_j:init_j + int(num_frames / num_frames_code)]
+
+    # ---- device scans ----------------------------------------------------------
+    def _scan(self, which: str, q: torch.Tensor, table: torch.Tensor, stream=None):
+        lib, db = _lib.load(), self.db
+        Q = q.shape[0]
+        sp = _lib.stream_ptr(stream)
+        _lib.check(lib.qpg_table_init(_lib.ptr(table), Q * codebook_size, sp), "qpg_table_init")
+        if which == "text" or db.mode == "A":
+            t = db.txt if which == "text" else db.aud
+            assert q.dtype == torch.float32 and q.shape[1] == t.D, (q.shape, t.D)
+            _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
+                                                     t.W, t.D, db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), 0, sp),
+                       "qpg_cand_cosine_minbycode")
+        else:
+            assert q.dtype == torch.int32 and q.shape[1] == 12
+            _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W, db.id_offset,
+                                                  _lib.ptr(q), Q, _lib.ptr(table), sp), "qpg_cand_lev_minbycode")
+        if self.process_group is not None:
+            table = self._merge_shards(table, stream)
+        return table
+
+    def _merge_shards(self, table, stream=None):
+        import torch.distributed as dist
+
+        lib = _lib.load()
+        world = dist.get_world_size(self.process_group)
+        parts = torch.empty((world,) + tuple(table.shape), dtype=table.dtype, device=table.device)
+        dist.all_gather_into_tensor(parts, table, group=self.process_group)
+        out = torch.empty_like(table)
+        _lib.check(lib.qpg_table_merge(_lib.ptr(parts), world, table.shape[0] * codebook_size, _lib.ptr(out),
+                                       _lib.stream_ptr(stream)), "qpg_table_merge")
+        return out
+
+    def _audio_query_tensor(self, aud_q: np.ndarray) -> torch.Tensor:
+        if self.db.mode == "A":
+            return torch.from_numpy(np.ascontiguousarray(aud_q, dtype=np.float32))
+        a = np.asarray(aud_q)
+        tok = wavvq_tokens(a) if a.shape[-1] == 22 else a
+        return torch.from_numpy(pad_tokens(tok).view(np.int32))
+
+    def match_tables(self, aud_q, txt_q):
+        """State-independent part for Q query steps: device tables [Q,512] of
+        (best distance, best global window id) for audio and text."""
+        dev = self.db.device
+        with torch.cuda.device(dev):
+            qa = self._audio_query_tensor(aud_q).to(dev, non_blocking=True)
+            qt = torch.from_numpy(np.ascontiguousarray(txt_q, dtype=np.float32)).to(dev, non_blocking=True)
+            ta = self._scan("audio", qa, new_table(qa.shape[0], dev))
+            tt = self._scan("text", qt, new_table(qt.shape[0], dev))
+        return ta, tt
+
+    def _lists_from_table(self, row: np.ndarray, which: str):
+        dist = [float(x) for x in row["d"]]
+        index, aux = [], []
+        for w in row["id"]:
+            if w < 0:
+                index.append([])
+                aux.append([])
+            else:
+                index.append(self.db.payload(w))
+                aux.append(self.db.aux(w, which))
+        return dist, index, aux
+
+    def search_audio_cands(self, clip_input, mode="audio"):
+        """GestureKNN.py:666-691 for mode 'wavlm_feat' / 'wavvq_feat'."""
+        want = {"A": "wavlm_feat", "B": "wavvq_feat"}[self.db.mode]
+        if mode != want:
+            raise NotImplementedError(f"database was built for mode {want!r}, got {mode!r}")
+        dev = self.db.device
+        with torch.cuda.device(dev):
+            q = self._audio_query_tensor(np.asarray(clip_input)[None, :]).to(dev)
+            table = self._scan("audio", q, new_table(1, dev))
+        return self._lists_from_table(table_to_numpy(table)[0], "audio")
+
+    def search_text_cands(self, clip_input, mode="wavvq_feat"):
+        """GestureKNN.py:708-721."""
+        dev = self.db.device
+        with torch.cuda.device(dev):
+            q = torch.from_numpy(np.ascontiguousarray(np.asarray(clip_input)[None, :], dtype=np.float32)).to(dev)
+            table = self._scan("text", q, new_table(1, dev))
+        return self._lists_from_table(table_to_numpy(table)[0], "text")
+
+    # ---- sequential tail ---------------------------------------------------------
+    def tail_device(self, ta, tt, seed_code, seed_phase, n_clips, n_seg, want_phase=True):
+        """ranks + match_tail kernels for n_clips x n_seg x 8 steps already scanned."""
+        lib, db, dev = _lib.load(), self.db, self.db.device
+        Q = n_clips * n_seg * STEPS_PER_SEGMENT
+        assert ta.shape[0] == Q and tt.shape[0] == Q
+        with torch.cuda.device(dev):
+            sp = _lib.stream_ptr()
+            ra = torch.empty((Q, codebook_size), dtype=torch.int32, device=dev)
+            rt = torch.empty((Q, codebook_size), dtype=torch.int32, device=dev)
+            _lib.check(lib.qpg_rank512(_lib.ptr(ta), Q, _lib.ptr(ra), sp), "qpg_rank512")
+            _lib.check(lib.qpg_rank512(_lib.ptr(tt), Q, _lib.ptr(rt), sp), "qpg_rank512")
+            sc = torch.as_tensor(np.asarray(seed_code, dtype=np.int32).reshape(n_clips), device=dev)
+            sph = torch.as_tensor(np.ascontiguousarray(seed_phase, dtype=np.float32).reshape(n_clips, 8, 16), device=dev)
+            codes = torch.empty((n_clips, n_seg, num_frames_code), dtype=torch.int64, device=dev)
+            vote = torch.empty((n_clips, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
+            status = torch.empty((n_clips,), dtype=torch.int32, device=dev)
+            phase = torch.empty((n_clips, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
+                if want_phase else None
+            _lib.check(lib.qpg_match_tail(_lib.ptr(ta), _lib.ptr(tt), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(db.pos_rank),
+                                          _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
+                                          _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(sc), _lib.ptr(sph),
+                                          n_clips, n_seg, _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(phase),
+                                          _lib.ptr(status), sp), "qpg_match_tail")
+        return codes, vote, phase, status
+
+    def _tail_numpy_segment(self, ta_np, tt_np, seed_code, seed_phase, desired_k=0, use_txt=True, use_aud=True):
+        """The reference's own per-step NumPy calls (GestureKNN.py:528-660) on the
+        device-computed tables -- inherits NumPy's tie order on this machine."""
+        from sklearn.metrics.pairwise import paired_distances
+
+        db = self.db
+        result, result_phase, vote = [int(seed_code)], [np.asarray(seed_phase)], []
+        for s in range(ta_np.shape[0]):
+            pos_score = db.pos_rank_host[result[-1]].astype(np.int64)
+            pos_score = pos_score + db.freq_rank_host.astype(np.int64) * 0.05
+            picks = []
+            if use_aud:
+                aud_score = np.array([float(x) for x in ta_np[s]["d"]]).argsort().argsort()
+                idx = np.argsort(pos_score + aud_score).tolist()
+                picks += [("audio", ta_np[s], i) for i in (idx[:1] if use_txt else idx[:2])]
+            if use_txt:
+                txt_score = np.array([float(x) for x in tt_np[s]["d"]]).argsort().argsort()
+                idx_ = np.argsort(pos_score + txt_score).tolist()
+                picks += [("text", tt_np[s], i) for i in (idx_[:1] if use_aud else idx_[:2])]
+            tmp_distance, tmp_phase_amp, wins = [], [], []
+            for which, tab, c in picks:
+                w = int(tab["id"][c])
+                if w < 0:
+                    raise IndexError("list index out of range")       # reference: aux[index] == [] at :631
+                j, k = db.aux(w, which)
+                f = int(k / 398 * 240)
+                win = db.phase_amp_host[j, f:f + 32]
+                head = win[:8]
+                a = np.concatenate((result_phase[-1][-5:], head[:3]), axis=0).reshape(-1)
+                b = np.concatenate((result_phase[-1][-3:], head[:5]), axis=0).reshape(-1)
+                tmp_distance.append(paired_distances([a], [b], metric="cosine")[0])
+                tmp_phase_amp.append(win[-8:])
+                wins.append(w)
+            final_index = tmp_distance.index(min(tmp_distance))
+            result.extend(int(x) for x in db.payload(wins[final_index]))
+            result_phase.append(tmp_phase_amp[final_index])
+            vote.append(final_index)
+        return (np.array(result)[1:1 + num_frames_code], np.array(result_phase[1:]), np.array(vote))
+
+    def search_code_knn(self, clip_test, desired_k, use_feature=False, use_wavlm=False, use_freq=False,
+                        seed_code=None, use_wavvq=False, use_phase=False, seed_phase=None, use_txt=False,
+                        clip_context=None, use_aud=False):
+        """One 4-s segment (GestureKNN.py:501-664).  clip_test: (180, 6C) stacked WavLM
+        feature in mode A, (398, 22) stacked wavvq feature in mode B; clip_context (30, Dt)."""
+        if not (use_phase and use_feature):
+            raise NotImplementedError("only the phase-guided feature matcher (GestureKNN.py:842-843) is built")
+        if not (use_aud or use_txt):
+            raise ValueError("need use_aud and/or use_txt")
+        clip_test = np.asarray(clip_test)
+        if seed_code is not None:
+            init_code, init_phase_amp = seed_code, seed_phase
+        else:
+            init_code, init_phase_amp = self.init_code_phase()
+        n = len(clip_test)
+        i_list, i = [], 0
+        while i < n:                                                   # :528, :659
+            i_list.append(i)
+            i += STEP_SZ * self.step_sz
+        aud_q = clip_test[[int(i) for i in i_list]]
+        denom = n if self.db.mode == "A" else 398                       # :548-551
+        ctx = np.asarray(clip_context)
+        txt_q = ctx[[int(i / denom * 30) for i in i_list]]
+        ta, tt = self.match_tables(aud_q, txt_q)
+        if self.tail == "device" and use_aud and use_txt and len(i_list) == STEPS_PER_SEGMENT:
+            codes, vote, phase, status = self.tail_device(ta, tt, [init_code], np.asarray(init_phase_amp)[None], 1, 1)
+            if int(status.cpu()[0]) != 0:
+                raise IndexError("list index out of range")           # same failure as GestureKNN.py:631
+            return codes[0, 0].cpu().numpy(), phase[0, 0].cpu().numpy(), vote[0, 0].cpu().numpy()
+        return self._tail_numpy_segment(table_to_numpy(ta), table_to_numpy(tt), init_code, init_phase_amp,
+                                        desired_k, use_txt=use_txt, use_aud=use_aud)
+
+    # ---- batched entry: many clips at once ---------------------------------------
+    def match_clips(self, aud_q, txt_q, seed_code=None, seed_phase=None, tail=None):
+        """aud_q [n_clips, n_seg, 8, Da] (or tokens [..., 11|22]), txt_q [n_clips, n_seg, 8, Dt]
+        (host arrays).  Returns int64 codes [n_clips, n_seg, 30] on the host."""
+        tail = tail or self.tail
+        aud_q, txt_q = np.asarray(aud_q), np.asarray(txt_q)
+        n_clips, n_seg = aud_q.shape[0], aud_q.shape[1]
+        Q = n_clips * n_seg * STEPS_PER_SEGMENT
+        if seed_code is None:
+            seeds = [self.init_code_phase() for _ in range(n_clips)]
+            seed_code = [s[0] for s in seeds]
+            seed_phase = np.stack([s[1] for s in seeds])
+        ta, tt = self.match_tables(aud_q.reshape((Q,) + aud_q.shape[3:]), txt_q.reshape(Q, -1))
+        if tail == "device":
+            codes, vote, _, status = self.tail_device(ta, tt, seed_code, seed_phase, n_clips, n_seg, want_phase=False)
+            codes_h = codes.cpu().numpy()
+            if int(status.max().cpu()) != 0:
+                raise IndexError("list index out of range")
+            return codes_h
+        ta_np = table_to_numpy(ta).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)
+        tt_np = table_to_numpy(tt).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)
+        out = np.empty((n_clips, n_seg, num_frames_code), dtype=np.int64)
+        for b in range(n_clips):
+            code0, ph0 = seed_code[b], np.asarray(seed_phase[b])
+            for g in range(n_seg):
+                codes, phases, _ = self._tail_numpy_segment(ta_np[b, g], tt_np[b, g], code0, ph0)
+                out[b, g] = codes
+                code0, ph0 = int(codes[-1]), phases[-1]
+        return out
+
+
+def _phase_ntc(phase_train):
+    """CodeKNN receives phase as (N, 240, 4[, 8]); accept the (N, 4, 240[, 8]) layout
+    load_db_codebook returns as well."""
+    p = phase_train
+    if isinstance(p, np.ndarray) and p.ndim >= 3 and p.shape[1] == 4 and p.shape[2] != 4:
+        p = np.swapaxes(p, 1, 2)
+    return p
+
+
+# --------------------------------------------------------------------------
+def predict_code_from_audio(train_mfcc, train_code, test_mfcc, data_stats, train_feat, test_feat, train_wavlm,
+                            test_wavlm, train_wavlm_feat, test_wavlm_feat, speech_features, test_speech_features,
+                            train_speech_features_feat, test_speech_features_feat, train_wavvq_feat, test_wavvq_feat,
+                            train_phase, test_phase, train_context, test_context, use_feature=False, use_wavlm=False,
+                            use_freq=False, use_speechfeat=False, use_wavvq=False, use_phase=False, use_txt=False,
+                            use_aud=False, frames=0, **knn_kwargs):
+    """GestureKNN.py:724-813 with the reference's positional arguments (arrays in
+    (N, feat, time) order as load_db_codebook returns them).  Segments are chained
+    through (last code, last phase) exactly as :791,:800."""
+    tr = lambda a: None if a is None else np.asarray(a).transpose((0, 2, 1))
+    n_test_seq = frames if frames != 0 else test_wavvq_feat.shape[0]                    # :740
+    knn = CodeKNN(code_train=train_code, wavlm_train=tr(train_wavlm), wavlm_train_feat=tr(train_wavlm_feat),
+                  wavvq_train_feat=tr(train_wavvq_feat), phase_train=_phase_ntc(train_phase),
+                  context_train=tr(train_context), use_wavlm=use_wavlm, use_wavvq=use_wavvq, use_phase=use_phase,
+                  use_txt=use_txt, **knn_kwargs)
+    clips = tr(test_wavlm_feat) if use_wavlm else tr(test_wavvq_feat)
+    ctx = tr(test_context)
+    motion_output, phase_output = [], []
+    for i in range(n_test_seq):
+        pred_motion, pred_phase, _ = knn.search_code_knn(
+            clip_test=clips[i], desired_k=(args.desired_k if args is not None else 0), use_wavlm=use_wavlm,
+            use_feature=use_feature, use_freq=use_freq, seed_code=motion_output[-1][-1] if i > 0 else None,
+            use_wavvq=use_wavvq, use_phase=use_phase, seed_phase=phase_output[-1][-1] if i > 0 else None,
+            use_txt=use_txt, clip_context=ctx[i] if use_txt else None, use_aud=use_aud)
+        motion_output.append(pred_motion)
+        phase_output.append(pred_phase)
+    return np.array(motion_output)
+
+
+def build_knn_from_files(a, mode="A", tail="device", device=None, seq_range=None, process_group=None):
+    """Lean construction used by the CLI and the bench: reads the 8 npz files and
+    uploads only what the shipped matcher scans."""
+    from .data_processing import load_match_inputs
+
+    inp = load_match_inputs(a.train_database, a.train_codebook, a.test_data, a.train_wavlm, a.test_wavlm,
+                            a.train_wavvq, a.test_wavvq, mode=mode)
+    signature = np.load(a.codebook_signature)["signature"]
+    db = MatchDatabase(mode, inp["code"], signature, phase_to_dense(inp["phase"]), inp["txt_rows"],
+                       aud_rows=inp.get("aud_rows"), aud_tokens=inp.get("aud_tokens"),
+                       freq_code=np.load(a.train_codebook)["code"], device=device, seq_range=seq_range)
+    knn = CodeKNN(database=db, use_wavlm=mode == "A", use_wavvq=mode == "B", use_phase=True, use_txt=True, tail=tail,
+                  process_group=process_group)
+    return knn, inp
+
+
+def main_codebook(maxFrames=0, mode=None, tail=None):
+    """GestureKNN.py:816-845: load, match every test segment, write knn_pred."""
+    mode = mode or getattr(args, "mode", "A")
+    tail = tail or getattr(args, "tail", "device")
+    device = torch.device("cuda", getattr(args, "gpu", 0))
+    knn, inp = build_knn_from_files(args, mode=mode, tail=tail, device=device)
+    n_test_seq = maxFrames if maxFrames != 0 else inp["n_test"]                            # :740
+    aud_q, txt_q = inp["aud_q"][:n_test_seq], inp["txt_q"][:n_test_seq]
+    pred_seqs = knn.match_clips(aud_q[None], txt_q[None], tail=tail)[0]
+    print(pred_seqs.shape)
+    os.makedirs(os.path.dirname(os.path.abspath(args.out_knn_filename)), exist_ok=True)
+    np.savez_compressed(args.out_knn_filename, knn_pred=pred_seqs)
+    return pred_seqs
+
+
+def main(argv=None):
+    set_args(build_parser().parse_args(argv))
+    seed_everything()
+    return main_codebook(maxFrames=args.max_frames)
+
+
+if __name__ == "__main__":
+    main()

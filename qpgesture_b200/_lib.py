@@ -1,0 +1,97 @@
+"""ctypes binding of libqpg_sm100.so (C ABI declared in include/qpg.h).
+
+The product path has no CPU fallback: if the library is missing, or a call
+fails, this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libqpg_sm100.so")
+
+_lib = None
+
+
+class QpgError(RuntimeError):
+    pass
+
+
+class ConvDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T_in", C.c_int), ("T_out_total", C.c_int), ("C_in", C.c_int), ("C_out", C.c_int),
+        ("n_taps", C.c_int), ("tap_offset", C.c_int * 4), ("in_stride", C.c_int), ("out_stride", C.c_int),
+        ("out_offset", C.c_int), ("n_out", C.c_int), ("relu_in", C.c_int), ("precision", C.c_int),
+    ]
+
+
+_P = C.c_void_p
+_I64 = C.c_int64
+_INT = C.c_int
+
+# name -> (restype, argtypes); every symbol include/qpg.h declares
+SIGNATURES = {
+    "qpg_version": (_INT, []),
+    "qpg_last_error": (C.c_char_p, []),
+    "qpg_launch_count": (C.c_uint64, []),
+    "qpg_tune_cosine": (_INT, [_INT, _INT, _INT]),
+    "qpg_packed_bytes": (C.c_size_t, [_I64, _INT]),
+    "qpg_pack_rows_f32": (_INT, [_P, _I64, _INT, _P, _P, _P]),
+    "qpg_table_init": (_INT, [_P, _I64, _P]),
+    "qpg_cand_cosine_minbycode": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _P]),
+    "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
+    "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
+    "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),
+    "qpg_rank512": (_INT, [_P, _INT, _P, _P]),
+    "qpg_match_tail": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
+    "qpg_vq_argmin_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
+    "qpg_vq_dequantise_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P]),
+    "qpg_conv1d_taps_f32": (_INT, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+}
+
+
+def load():
+    """Load the native library (once).  Raises QpgError when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise QpgError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C qpgesture_b200/csrc`). There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().qpg_last_error().decode("utf-8", "replace")
+        raise QpgError(f"{what} failed (rc={rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise QpgError("expected a CUDA tensor")
+    if not t.is_contiguous():
+        raise QpgError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return C.c_void_p(s.cuda_stream)
+
+
+def launch_count() -> int:
+    return int(load().qpg_launch_count())

@@ -1,0 +1,383 @@
+// Candidate-distance kernel: cosine distance of up to 8 queries against every
+// database window, fused with the reference's "best window per start-code"
+// reduction (GestureKNN.py:666-691 mode 'wavlm_feat', :708-721).
+//
+// Roofline: HBM bandwidth.  One launch = one pass over the packed window table
+// (W * 4 * ceil128(D) bytes) for QT queries; arithmetic is 1 F2F + QT DFMA per
+// database element (float64 accumulation of float32 data so that the selected
+// window ids equal the reference's float64 sklearn path).
+//
+// Data movement: the table is stored as 4 KiB tiles [8 rows][128 floats]
+// (qpg_pack_rows_f32); every warp owns a contiguous run of row groups, streams
+// its tiles through a private NS-deep shared-memory ring with TMA bulk copies
+// (cp.async.bulk -> UBLKCP) completing on mbarriers, and refills a slot as soon
+// as it has consumed it.  Queries live in shared memory for the whole launch.
+// Per row group the 8xQT partial dot products are transposed-reduced with warp
+// shuffles so that each lane ends up owning one (row, query) pair; it computes
+// the distance and does a lexicographic (distance, window id) atomic min
+// (128-bit CAS) into the CTA's [QT][512] table, which is merged into the global
+// table at the end of the launch.
+#include "qpg_common.cuh"
+
+namespace qpg {
+namespace {
+
+constexpr int R = QPG_ROWS_PER_GROUP;  // 8 rows per tile
+constexpr int DC = QPG_CHUNK;          // 128 floats per tile row
+constexpr int TILE_FLOATS = R * DC;    // 1024
+constexpr int TILE_BYTES = TILE_FLOATS * 4;
+constexpr int KB = QPG_CODEBOOK_SIZE;
+constexpr size_t kSmemLimit = 232448;  // 227 KiB opt-in limit per CTA on sm_100
+
+// ------------------------------------------------------------------ pack ----
+// One CTA (8 warps) per row group; warp r owns row 8g+r.
+__global__ void __launch_bounds__(256) pack_rows_kernel(const float* __restrict__ rows, int64_t W, int D,
+                                                        int NC, float* __restrict__ packed,
+                                                        double* __restrict__ row_sqnorm) {
+  const int64_t g = blockIdx.x;
+  const int r = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = g * R + r;
+  const bool live = row < W;
+  const float* src = rows + row * (int64_t)D;
+  double acc = 0.0;
+  for (int c = 0; c < NC; ++c) {
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    const int d0 = c * DC + 4 * lane;
+    if (live) {
+      if (d0 + 0 < D) v.x = src[d0 + 0];
+      if (d0 + 1 < D) v.y = src[d0 + 1];
+      if (d0 + 2 < D) v.z = src[d0 + 2];
+      if (d0 + 3 < D) v.w = src[d0 + 3];
+    }
+    acc = fma((double)v.x, (double)v.x, acc);
+    acc = fma((double)v.y, (double)v.y, acc);
+    acc = fma((double)v.z, (double)v.z, acc);
+    acc = fma((double)v.w, (double)v.w, acc);
+    float4* dst = reinterpret_cast<float4*>(packed + ((g * NC + c) * R + r) * (int64_t)DC) + lane;
+    *dst = v;
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0 && live) row_sqnorm[row] = acc;
+}
+
+__global__ void table_init_kernel(Pair* t, int64_t n) {
+  int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) {
+    Pair p;
+    p.d = (unsigned long long)__double_as_longlong(kEmptyDist);
+    p.id = ~0ull;
+    t[i] = p;
+  }
+}
+
+// ------------------------------------------------- transposed warp reduce ----
+// V partial sums per lane -> after log2 steps lane l owns total #(l*V/32 ...):
+// V=64: totals 2l,2l+1 ; V=32: total l ; V=16: total l>>1 ; V=8: total l>>2.
+template <int V, int O>
+struct TransposeReduce {
+  static __device__ __forceinline__ void run(double* v, int lane) {
+    if constexpr (O >= 1) {
+      if constexpr (V > 1) {
+        constexpr int half = V / 2;
+        const bool upper = (lane & O) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+          const double send = upper ? v[i] : v[i + half];
+          const double keep = upper ? v[i + half] : v[i];
+          v[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+        }
+        TransposeReduce<half, O / 2>::run(v, lane);
+      } else {
+        v[0] += __shfl_xor_sync(0xffffffffu, v[0], O);
+        TransposeReduce<1, O / 2>::run(v, lane);
+      }
+    }
+  }
+};
+
+__device__ __forceinline__ double cosine_distance(double dot, double sqq, double sqx) {
+  // sklearn: normalize() leaves an all-zero vector at zero (norm 0 -> 1), then
+  // 0.5*||a-b||^2 = 0.5*(|a|^2+|b|^2) - <a,b> with |a|,|b| in {0,1}.
+  const double a = sqq > 0.0 ? 1.0 : 0.0;
+  const double b = sqx > 0.0 ? 1.0 : 0.0;
+  double c = 0.0;
+  if (sqq > 0.0 && sqx > 0.0) c = dot / (sqrt(sqq) * sqrt(sqx));
+  double d = 0.5 * (a + b) - c;
+  return d < 0.0 ? 0.0 : d;
+}
+
+// ------------------------------------------------------------ main kernel ----
+template <int QT, int NCW>
+__global__ void __launch_bounds__(NCW * 32, 1)
+    cand_cosine_kernel(const float* __restrict__ packed, const double* __restrict__ row_sqnorm,
+                       const int32_t* __restrict__ labels, int64_t W, int D, int NC, int64_t G,
+                       int64_t id_offset, const float* __restrict__ q, int nq, Pair* __restrict__ table,
+                       int NS) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int Dp = NC * DC;
+  float* ring = reinterpret_cast<float*>(smem_raw);                        // [NCW][NS][1024]
+  float* qs = ring + (size_t)NCW * NS * TILE_FLOATS;                       // [QT][Dp]
+  Pair* tab = reinterpret_cast<Pair*>(qs + (size_t)QT * Dp);               // [QT][512]
+  double* qn = reinterpret_cast<double*>(tab + QT * KB);                   // [QT] squared norms
+  uint64_t* bars = reinterpret_cast<uint64_t*>(qn + 8);                    // [NCW][NS]
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nthreads = NCW * 32;
+
+  // ---- prologue: queries, table, barriers
+  for (int i = tid; i < QT * Dp; i += nthreads) {
+    const int qi = i / Dp, d = i - qi * Dp;
+    qs[i] = (qi < nq && d < D) ? q[(size_t)qi * D + d] : 0.f;
+  }
+  for (int i = tid; i < QT * KB; i += nthreads) {
+    Pair p;
+    p.d = (unsigned long long)__double_as_longlong(kEmptyDist);
+    p.id = ~0ull;
+    tab[i] = p;
+  }
+  if (tid < NCW * NS) mbar_init(&bars[tid], 1);
+  fence_mbar_init();
+  __syncthreads();
+  if (warp < QT) {
+    double s = 0.0;
+    for (int d = lane; d < Dp; d += 32) {
+      const double v = (double)qs[warp * Dp + d];
+      s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) qn[warp] = s;
+  }
+  __syncthreads();
+
+  // ---- this warp's contiguous run of row groups
+  const int64_t slot = (int64_t)blockIdx.x * NCW + warp;
+  const int64_t nslots = (int64_t)gridDim.x * NCW;
+  const int64_t g0 = slot * G / nslots, g1 = (slot + 1) * G / nslots;
+  const int64_t n_tiles = (g1 - g0) * NC;
+  const float* stream = packed + g0 * NC * (int64_t)TILE_FLOATS;
+  float* my_ring = ring + (size_t)warp * NS * TILE_FLOATS;
+  uint64_t* my_bars = bars + warp * NS;
+
+  if (lane == 0) {
+    for (int s = 0; s < NS && s < n_tiles; ++s) {
+      mbar_arrive_expect_tx(&my_bars[s], TILE_BYTES);
+      bulk_g2s(my_ring + (size_t)s * TILE_FLOATS, stream + (int64_t)s * TILE_FLOATS, TILE_BYTES, &my_bars[s]);
+    }
+  }
+
+  double acc[R * QT];
+#pragma unroll
+  for (int i = 0; i < R * QT; ++i) acc[i] = 0.0;
+
+  int s = 0, c = 0;
+  uint32_t parity = 0;
+  int64_t g = g0;
+  for (int64_t it = 0; it < n_tiles; ++it) {
+    mbar_wait(&my_bars[s], parity);
+    const float4* tile = reinterpret_cast<const float4*>(my_ring + (size_t)s * TILE_FLOATS) + lane;
+    float4 x[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) x[r] = tile[r * (DC / 4)];
+    float4 qv[QT];
+#pragma unroll
+    for (int qi = 0; qi < QT; ++qi)
+      qv[qi] = *reinterpret_cast<const float4*>(qs + (size_t)qi * Dp + c * DC + 4 * lane);
+
+#pragma unroll
+    for (int comp = 0; comp < 4; ++comp) {
+      double qd[QT];
+#pragma unroll
+      for (int qi = 0; qi < QT; ++qi)
+        qd[qi] = (double)(comp == 0 ? qv[qi].x : comp == 1 ? qv[qi].y : comp == 2 ? qv[qi].z : qv[qi].w);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const double xd = (double)(comp == 0 ? x[r].x : comp == 1 ? x[r].y : comp == 2 ? x[r].z : x[r].w);
+#pragma unroll
+        for (int qi = 0; qi < QT; ++qi) acc[r * QT + qi] = fma(xd, qd[qi], acc[r * QT + qi]);
+      }
+    }
+
+    // slot consumed by every lane -> refill it with tile it+NS
+    __syncwarp();
+    if (lane == 0 && it + NS < n_tiles) {
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&my_bars[s], TILE_BYTES);
+      bulk_g2s(my_ring + (size_t)s * TILE_FLOATS, stream + (it + NS) * (int64_t)TILE_FLOATS, TILE_BYTES,
+               &my_bars[s]);
+    }
+    if (++s == NS) {
+      s = 0;
+      parity ^= 1u;
+    }
+
+    if (++c == NC) {  // row group complete: reduce, distance, min-by-code
+      c = 0;
+      TransposeReduce<R * QT, 16>::run(acc, lane);
+      const int r = lane >> 2;
+      const int64_t row = g * R + r;
+      constexpr int PER_LANE = (R * QT >= 32) ? (R * QT) / 32 : 1;
+      constexpr int DUP = (R * QT >= 32) ? 1 : 32 / (R * QT);  // lanes holding the same total
+      if (row < W && (lane % DUP) == 0) {
+        const double sqx = row_sqnorm[row];
+        const int label = labels[row];
+        if ((unsigned)label < (unsigned)KB) {
+#pragma unroll
+          for (int j = 0; j < PER_LANE; ++j) {
+            const int idx = (R * QT >= 32) ? lane * PER_LANE + j : lane / DUP;
+            const int qi = idx % QT;
+            if (qi < nq) {
+              const double dist = cosine_distance(acc[j], qn[qi], sqx);
+              if (dist < kEmptyDist) {
+                Pair mine;
+                mine.d = (unsigned long long)__double_as_longlong(dist);
+                mine.id = (unsigned long long)(id_offset + row);
+                pair_min_shared(&tab[qi * KB + label], mine);
+              }
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < R * QT; ++i) acc[i] = 0.0;
+      ++g;
+    }
+  }
+
+  // ---- merge the CTA table into the global one
+  __syncthreads();
+  for (int i = tid; i < nq * KB; i += nthreads) {
+    const Pair e = tab[i];
+    if (e.id != ~0ull) pair_min_global(&table[i], e);
+  }
+}
+
+struct Tuning {
+  int ncw = 0;  // 0 = auto
+  int ns = 0;
+  int grid = 0;
+};
+Tuning g_tuning;
+
+template <int QT, int NCW>
+int launch_cosine(const float* packed, const double* row_sqnorm, const int32_t* labels, int64_t W, int D,
+                  int64_t id_offset, const float* q, int nq, Pair* table, int NS, int grid,
+                  cudaStream_t st) {
+  const int NC = (D + DC - 1) / DC;
+  const int64_t G = (W + R - 1) / R;
+  const size_t smem = (size_t)NCW * NS * TILE_BYTES + (size_t)QT * NC * DC * 4 + (size_t)QT * KB * sizeof(Pair) +
+                      8 * sizeof(double) + (size_t)NCW * NS * sizeof(uint64_t);
+  auto kern = cand_cosine_kernel<QT, NCW>;
+  QPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  kern<<<grid, NCW * 32, smem, st>>>(packed, row_sqnorm, labels, W, D, NC, G, id_offset, q, nq, table, NS);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+size_t fixed_smem(int QT, int D) {
+  const int NC = (D + DC - 1) / DC;
+  return (size_t)QT * NC * DC * 4 + (size_t)QT * KB * sizeof(Pair) + 8 * sizeof(double) + 1024;
+}
+
+}  // namespace
+
+int cosine_set_tuning(int ncw, int ns, int grid) {
+  g_tuning.ncw = ncw;
+  g_tuning.ns = ns;
+  g_tuning.grid = grid;
+  return QPG_OK;
+}
+
+}  // namespace qpg
+
+using namespace qpg;
+
+extern "C" size_t qpg_packed_bytes(int64_t W, int D) {
+  if (W < 0 || D <= 0) return 0;
+  const int64_t G = (W + R - 1) / R;
+  const int64_t NC = (D + DC - 1) / DC;
+  return (size_t)(G * NC) * TILE_BYTES;
+}
+
+extern "C" int qpg_pack_rows_f32(const float* rows, int64_t W, int D, float* packed, double* row_sqnorm,
+                                 void* stream) {
+  QPG_CHECK_ARG(W >= 0 && D > 0, "W >= 0 and D > 0");
+  if (W == 0) return QPG_OK;
+  QPG_CHECK_ARG(rows && packed && row_sqnorm, "null pointer");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed must be 128-byte aligned");
+  const int64_t G = (W + R - 1) / R;
+  const int NC = (D + DC - 1) / DC;
+  QPG_CHECK_ARG(G < (1ll << 31), "too many row groups");
+  pack_rows_kernel<<<(unsigned)G, 256, 0, (cudaStream_t)stream>>>(rows, W, D, NC, packed, row_sqnorm);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_table_init(qpg_pair_t* table, int64_t n_entries, void* stream) {
+  QPG_CHECK_ARG(n_entries >= 0, "n_entries >= 0");
+  if (n_entries == 0) return QPG_OK;
+  QPG_CHECK_ARG(table != nullptr, "null table");
+  const int64_t blocks = (n_entries + 255) / 256;
+  table_init_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<Pair*>(table), n_entries);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_cand_cosine_minbycode(const float* packed, const double* row_sqnorm, const int32_t* labels,
+                                         int64_t W, int D, int64_t id_offset, const float* q, int Q,
+                                         qpg_pair_t* table, int queries_per_pass, void* stream) {
+  QPG_CHECK_ARG(W >= 0 && D > 0 && Q >= 0, "W >= 0, D > 0, Q >= 0");
+  if (W == 0 || Q == 0) return QPG_OK;
+  QPG_CHECK_ARG(packed && row_sqnorm && labels && q && table, "null pointer");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 127) == 0, "packed must be 128-byte aligned");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(table) & 15) == 0, "table must be 16-byte aligned");
+  QPG_CHECK_ARG(queries_per_pass >= 0 && queries_per_pass <= 8, "queries_per_pass in 0..8");
+  cudaStream_t st = (cudaStream_t)stream;
+
+  // queries per pass: as many as fit next to >= 24 ring tiles, capped by Q
+  int qt = queries_per_pass ? queries_per_pass : 8;
+  while (qt > 1 && (qt / 2) >= Q) qt /= 2;  // do not carry idle query lanes
+  if (qt != 1 && qt != 2 && qt != 4 && qt != 8) qt = qt > 4 ? 4 : (qt > 2 ? 2 : 1);
+  while (qt > 1 && fixed_smem(qt, D) + 24 * TILE_BYTES > kSmemLimit) qt /= 2;
+  if (fixed_smem(qt, D) + 16 * TILE_BYTES > kSmemLimit) {
+    set_error("D=%d too large for the shared-memory query tile", D);
+    return QPG_E_UNSUPPORTED;
+  }
+  const int tiles_fit = (int)((kSmemLimit - fixed_smem(qt, D)) / TILE_BYTES);
+  int ncw = g_tuning.ncw ? g_tuning.ncw : (qt == 8 ? 8 : (tiles_fit >= 36 ? 12 : 8));
+  if (qt == 8) ncw = 8;
+  if (ncw != 8 && ncw != 12) ncw = 8;
+  int ns = g_tuning.ns ? g_tuning.ns : tiles_fit / ncw;
+  if (ns > 4) ns = 4;
+  if (ns * ncw > tiles_fit) ns = tiles_fit / ncw;
+  if (ns < 1) {
+    set_error("no room for a tile ring (D=%d)", D);
+    return QPG_E_UNSUPPORTED;
+  }
+  const int64_t G = (W + R - 1) / R;
+  int grid = g_tuning.grid ? g_tuning.grid : sm_count();
+  const int64_t max_useful = (G + ncw - 1) / ncw;
+  if (grid > max_useful) grid = (int)max_useful;
+  if (grid < 1) grid = 1;
+
+  Pair* tab = reinterpret_cast<Pair*>(table);
+  for (int q0 = 0; q0 < Q; q0 += qt) {
+    const int nq = (Q - q0) < qt ? (Q - q0) : qt;
+    const float* qp = q + (size_t)q0 * D;
+    Pair* tp = tab + (size_t)q0 * KB;
+    int rc;
+#define QPG_DISPATCH(QT_, NCW_)                                                                              \
+  rc = launch_cosine<QT_, NCW_>(packed, row_sqnorm, labels, W, D, id_offset, qp, nq, tp, ns, grid, st)
+    if (qt == 8) QPG_DISPATCH(8, 8);
+    else if (qt == 4 && ncw == 12) QPG_DISPATCH(4, 12);
+    else if (qt == 4) QPG_DISPATCH(4, 8);
+    else if (qt == 2 && ncw == 12) QPG_DISPATCH(2, 12);
+    else if (qt == 2) QPG_DISPATCH(2, 8);
+    else if (ncw == 12) QPG_DISPATCH(1, 12);
+    else QPG_DISPATCH(1, 8);
+#undef QPG_DISPATCH
+    if (rc != QPG_OK) return rc;
+  }
+  return QPG_OK;
+}

@@ -1,0 +1,231 @@
+"""Device-resident candidate database for the phase-guided matcher.
+
+What the reference keeps as Python/NumPy arrays inside CodeKNN
+(GestureKNN.py:423-460) is laid out here once per database for the B200
+kernels (DESIGN.md "Data layout in HBM"):
+
+  * audio windows  mode A: float32 [W, 6*C] stacked WavLM features of the 26
+                   candidate windows of every sequence (rows k = 0,6,...,150 of
+                   wavlm_train_feat, GestureKNN.py:671-690), packed into 4 KiB
+                   tiles + float64 squared norms
+                   mode B: uint32 [W, 12] vq-wav2vec tokens (GestureKNN.py:58-60)
+  * text windows   float32 [W, Dt] context_train[j, m] (GestureKNN.py:712-720)
+  * labels         int32 [W] start code code_train[j, m]
+  * code           int32 [N, 30];  phase_amp float32 [N, 240, 16]
+  * pos_rank       int32 [512, 512]  rank of ||sig[last]-sig[c]|| (:532-540)
+  * freq_rank      int32 [512]       rank of 1 - count/total (:481-499, :544)
+
+Window ids are global: id = 26*j + m over the WHOLE database, so that a
+row-sharded database (rank r holds sequences [j0, j1)) merges with a plain
+lexicographic min and ties keep the reference's scan order.
+"""
+from __future__ import annotations
+
+from collections import Counter
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from .constant import (STEP_SZ, WINDOWS_PER_SEQ, WAVVQ_FRAMES, codebook_size, num_frames, num_frames_code)
+
+PAIR_DTYPE = np.dtype([("d", "<f8"), ("id", "<i8")])
+
+
+# ----------------------------------------------------------------------------
+# host-side one-off tables (same NumPy expressions as the reference, so that
+# tie order inside argsort is whatever the reference gets on this machine)
+# ----------------------------------------------------------------------------
+def code_to_freq(train_code: np.ndarray) -> np.ndarray:
+    """CodeKNN.code_to_freq (GestureKNN.py:481-499) -> freq_dist_cands [512]."""
+    code = np.asarray(train_code).flatten()
+    result = Counter(code.tolist())
+    result_sorted = sorted(result.items(), key=lambda item: item[1], reverse=True)
+    x = [d[0] for d in result_sorted]
+    y = 1 - np.array([d[1] for d in result_sorted]) / sum(d[1] for d in result_sorted)
+    pos = {c: i for i, c in enumerate(x)}
+    return np.array([y[pos[i]] if i in pos else 1 for i in range(codebook_size)], dtype=np.float64)
+
+
+def freq_rank_from_code(train_code: np.ndarray) -> np.ndarray:
+    """np.array(freq_dist_cands).argsort().argsort() (GestureKNN.py:544)."""
+    return np.array(list(code_to_freq(train_code))).argsort().argsort().astype(np.int32)
+
+
+def pos_rank_table(signature: np.ndarray) -> np.ndarray:
+    """pos_score for every possible last code (GestureKNN.py:532-540):
+    row `last` = argsort(argsort([norm(sig[last]-sig[c]) or inf if c==last]))."""
+    sig = np.asarray(signature)
+    out = np.empty((codebook_size, codebook_size), dtype=np.int32)
+    for last in range(codebook_size):
+        pos = []
+        s_last = sig[last]
+        for c in range(codebook_size):
+            if c == last:
+                pos.append(1e10000)
+                continue
+            pos.append(np.linalg.norm(s_last - sig[c]))
+        out[last] = np.array(pos).argsort().argsort()
+    return out
+
+
+def phase_to_dense(phase) -> np.ndarray:
+    """phase column of the train npz -> float32 [N, 240, 16] = phase | amplitude
+    (columns 0 and 2 of the (p, f, a, b) tuple, GestureKNN.py:633-635).  Accepts the
+    reference's object array [N,240,4] of (1,8,1) tensors, or dense [N,240,4,8]."""
+    if isinstance(phase, np.ndarray) and phase.dtype != object:
+        ph = np.asarray(phase, dtype=np.float32)
+        assert ph.ndim == 4 and ph.shape[2] == 4, "dense phase must be [N,240,4,8]"
+        return np.ascontiguousarray(np.concatenate((ph[:, :, 0, :], ph[:, :, 2, :]), axis=2))
+    n, t = phase.shape[0], phase.shape[1]
+    out = np.empty((n, t, 16), dtype=np.float32)
+    for i in range(n):
+        for j in range(t):
+            out[i, j, :8] = phase[i, j, 0].detach().cpu().numpy().reshape(-1)
+            out[i, j, 8:] = phase[i, j, 2].detach().cpu().numpy().reshape(-1)
+    return out
+
+
+def mode_b_window_frames(n_db_frm: int = WAVVQ_FRAMES):
+    """int(k) and int(k/step_sz) of the float loop GestureKNN.py:671-690 (mode B)."""
+    step = n_db_frm / num_frames_code
+    ks, ms = [], []
+    k = 0
+    while k < n_db_frm - STEP_SZ * step:
+        ks.append(int(k))
+        ms.append(int(k / step))
+        k += step
+    return ks, ms
+
+
+def wavvq_tokens(feat22: np.ndarray) -> np.ndarray:
+    """[..., 22] stacked wavvq feature -> [..., 11] tokens g0*320+g1 (GestureKNN.py:58-60)."""
+    f = np.asarray(feat22).reshape(feat22.shape[:-1] + (-1, 2))
+    return (f[..., 0] * 320 + f[..., 1]).astype(np.int64)
+
+
+def pad_tokens(tok: np.ndarray) -> np.ndarray:
+    out = np.zeros(tok.shape[:-1] + (12,), dtype=np.uint32)
+    out[..., :11] = tok.astype(np.uint32)
+    return out
+
+
+def phase_frame(k) -> int:
+    return int(k / 398 * 240)  # GestureKNN.py:632,640 (398 is used in WavLM mode too)
+
+
+# ----------------------------------------------------------------------------
+@dataclass
+class PackedRows:
+    """float32 row table in the tile layout of qpg_pack_rows_f32."""
+    packed: torch.Tensor      # float32 [G*NC*1024]
+    sqnorm: torch.Tensor      # float64 [W]
+    W: int
+    D: int
+
+    @staticmethod
+    def from_rows(rows: torch.Tensor) -> "PackedRows":
+        lib = _lib.load()
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 2
+        rows = rows.contiguous()
+        W, D = rows.shape
+        nbytes = lib.qpg_packed_bytes(W, D)
+        packed = torch.empty(max(nbytes // 4, 1), dtype=torch.float32, device=rows.device)
+        sqnorm = torch.empty(max(W, 1), dtype=torch.float64, device=rows.device)
+        with torch.cuda.device(rows.device):
+            _lib.check(lib.qpg_pack_rows_f32(_lib.ptr(rows), W, D, _lib.ptr(packed), _lib.ptr(sqnorm),
+                                             _lib.stream_ptr()), "qpg_pack_rows_f32")
+        return PackedRows(packed, sqnorm[:W], W, D)
+
+    @property
+    def nbytes(self) -> int:
+        return self.packed.numel() * 4
+
+
+class MatchDatabase:
+    """Everything the matcher kernels read, resident on one GPU."""
+
+    def __init__(self, mode: str, code: np.ndarray, signature: np.ndarray, phase_amp: np.ndarray,
+                 txt_rows: np.ndarray, aud_rows: Optional[np.ndarray] = None,
+                 aud_tokens: Optional[np.ndarray] = None, freq_code: Optional[np.ndarray] = None,
+                 freq_rank: Optional[np.ndarray] = None, pos_rank: Optional[np.ndarray] = None,
+                 device=None, seq_range=None):
+        """aud_rows [N*26, Da] float32 (mode A) or aud_tokens [N*26, 11] ints (mode B);
+        txt_rows [N*26, Dt] float32.  `seq_range=(j0, j1)` keeps only the windows of
+        sequences j0..j1-1 on this GPU (row shard); code / phase tables stay whole."""
+        assert mode in ("A", "B")
+        _lib.load()
+        self.mode = mode
+        self.device = torch.device(device if device is not None else "cuda")
+        code = np.asarray(code)
+        self.n_seq = int(code.shape[0])
+        self.code_host = code.astype(np.int64)
+        self.signature = np.asarray(signature)
+        j0, j1 = (0, self.n_seq) if seq_range is None else seq_range
+        self.seq_range = (int(j0), int(j1))
+        self.id_offset = int(j0) * WINDOWS_PER_SEQ
+        w0, w1 = j0 * WINDOWS_PER_SEQ, j1 * WINDOWS_PER_SEQ
+        self.W = w1 - w0
+        dev = self.device
+
+        labels = code[:, :WINDOWS_PER_SEQ].reshape(-1).astype(np.int32)          # code_train[j, m]
+        self.labels = torch.from_numpy(np.ascontiguousarray(labels[w0:w1])).to(dev)
+        self.code = torch.from_numpy(code.astype(np.int32)).contiguous().to(dev)
+        self.phase_amp_host = np.ascontiguousarray(phase_amp, dtype=np.float32)
+        assert self.phase_amp_host.shape == (self.n_seq, num_frames, 16)
+        self.phase_amp = torch.from_numpy(self.phase_amp_host).to(dev)
+
+        txt = np.ascontiguousarray(np.asarray(txt_rows, dtype=np.float32)[w0:w1])
+        self.txt = PackedRows.from_rows(torch.from_numpy(txt).to(dev))
+        self.aud = None
+        self.tokens = None
+        if mode == "A":
+            aud = np.ascontiguousarray(np.asarray(aud_rows)[w0:w1], dtype=np.float32)
+            self.aud = PackedRows.from_rows(torch.from_numpy(aud).to(dev))
+            self.aud_k = [m * 6 for m in range(WINDOWS_PER_SEQ)]                    # k = 0,6,...,150
+            self.n_db_frm, self.step_sz = 180, 6
+        else:
+            tok = pad_tokens(np.asarray(aud_tokens)[w0:w1])
+            self.tokens = torch.from_numpy(tok.view(np.int32)).to(dev)             # bit pattern of uint32
+            ks, ms = mode_b_window_frames()
+            assert len(ks) == WINDOWS_PER_SEQ and ms == list(range(WINDOWS_PER_SEQ))
+            self.aud_k = ks
+            self.n_db_frm, self.step_sz = WAVVQ_FRAMES, WAVVQ_FRAMES / num_frames_code
+        self.txt_k = [m * 8 for m in range(WINDOWS_PER_SEQ)]                        # k = 0,8,...,200
+        self.aud_frame = torch.tensor([phase_frame(k) for k in self.aud_k], dtype=torch.int32, device=dev)
+        self.txt_frame = torch.tensor([phase_frame(k) for k in self.txt_k], dtype=torch.int32, device=dev)
+
+        if freq_rank is None:
+            freq_rank = freq_rank_from_code(code if freq_code is None else freq_code)
+        if pos_rank is None:
+            pos_rank = pos_rank_table(self.signature)
+        self.freq_rank_host = np.asarray(freq_rank, dtype=np.int32)
+        self.pos_rank_host = np.asarray(pos_rank, dtype=np.int32)
+        self.freq_rank = torch.from_numpy(self.freq_rank_host).to(dev)
+        self.pos_rank = torch.from_numpy(np.ascontiguousarray(self.pos_rank_host)).to(dev)
+        torch.cuda.synchronize(dev)
+
+    # -- bytes one query pass reads (the roofline's algorithmic bytes use D, not the padded D)
+    def algorithmic_bytes(self, which: str) -> int:
+        t = self.aud if which == "audio" else self.txt
+        return self.W * (4 * t.D + 4)
+
+    def payload(self, w: int) -> np.ndarray:
+        j, m = divmod(int(w), WINDOWS_PER_SEQ)
+        return self.code_host[j, m:m + STEP_SZ]
+
+    def aux(self, w: int, which: str):
+        j, m = divmod(int(w), WINDOWS_PER_SEQ)
+        return [j, int((self.aud_k if which == "audio" else self.txt_k)[m])]
+
+
+def new_table(Q: int, device) -> torch.Tensor:
+    """Uninitialised [Q, 512] table of qpg_pair_t (stored as int64 [Q,512,2])."""
+    return torch.empty((Q, codebook_size, 2), dtype=torch.int64, device=device)
+
+
+def table_to_numpy(table: torch.Tensor) -> np.ndarray:
+    """-> structured array [Q, 512] with fields d (float64) and id (int64)."""
+    return table.cpu().numpy().view(PAIR_DTYPE).reshape(table.shape[0], codebook_size)

@@ -1,0 +1,114 @@
+"""Synthetic databases in the reference's on-disk npz formats.
+
+There is no BEAT data, no checkpoint and no network, so every test and the
+bench run on seeded synthetic tensors of the named shapes.  File formats and
+keys follow codebook/Speech2GestureMatching/data_processing.py:200-206,255,
+278,339-343 and GestureKNN.py:476,483 so that both the reference (imported in
+place by oracle/ref_harness.py) and this package read the same files.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass
+
+import numpy as np
+
+from .constant import codebook_size, num_frames, num_frames_code, NUM_JOINTS, WAVVQ_FRAMES
+
+
+@dataclass
+class SynthPaths:
+    train_database: str
+    test_data: str
+    train_codebook: str
+    codebook_signature: str
+    train_wavlm: str
+    test_wavlm: str
+    train_wavvq: str
+    test_wavvq: str
+
+    def as_argv(self, out_knn_filename: str, max_frames: int = 0):
+        """The 11 flags GestureKNN.sh:7-18 passes."""
+        return [
+            f"--train_database={self.train_database}",
+            f"--test_data={self.test_data}",
+            f"--out_knn_filename={out_knn_filename}",
+            "--out_video_path=./output/output_video_folder/",
+            f"--train_codebook={self.train_codebook}",
+            f"--codebook_signature={self.codebook_signature}",
+            f"--train_wavlm={self.train_wavlm}",
+            f"--test_wavlm={self.test_wavlm}",
+            f"--train_wavvq={self.train_wavvq}",
+            f"--test_wavvq={self.test_wavvq}",
+            f"--max_frames={max_frames}",
+        ]
+
+
+def make_arrays(n_train: int, n_test: int, seed: int = 0, wavlm_dim: int = 1024,
+                ctx_dim: int = 384, wavlm_frames: int = 199, n_codes_used: int = codebook_size,
+                mfcc_dim: int = 14):
+    """Seeded arrays of the reference shapes.  `phase` is returned as a plain
+    float32 array [n, 240, 4, 8] (p, f, a, b channels); `phase_to_object`
+    turns it into the object array of (1,8,1) torch tensors the reference
+    pickles (data_processing.py:339)."""
+    rng = np.random.default_rng(seed)
+
+    def split(n):
+        return dict(
+            mfcc=rng.standard_normal((n, num_frames, mfcc_dim)).astype(np.float32),
+            energy=rng.standard_normal((n, num_frames)).astype(np.float32),
+            pitch=rng.standard_normal((n, num_frames)).astype(np.float32),
+            volume=rng.standard_normal((n, num_frames)).astype(np.float32),
+            phase=rng.standard_normal((n, num_frames, 4, 8)).astype(np.float32),
+            context=rng.standard_normal((n, num_frames_code, 1, ctx_dim)).astype(np.float32),
+            wavlm=rng.standard_normal((n, wavlm_frames, wavlm_dim)).astype(np.float32),
+            wavvq=rng.integers(0, 320, size=(n, WAVVQ_FRAMES, 2)).astype(np.int64),
+        )
+
+    train = split(n_train)
+    test = split(n_test)
+    code = rng.integers(0, n_codes_used, size=(n_train, num_frames_code)).astype(np.int64)
+    signature = rng.standard_normal((codebook_size, NUM_JOINTS)).astype(np.float32)
+    return train, test, code, signature
+
+
+def phase_to_object(phase: np.ndarray) -> np.ndarray:
+    """float32 [n, 240, 4, 8] -> object [n, 240, 4] of torch tensors (1, 8, 1)."""
+    import torch
+
+    n, t, c, ch = phase.shape
+    out = np.empty((n, t, c), dtype=object)
+    tens = torch.from_numpy(np.ascontiguousarray(phase))
+    for i in range(n):
+        for j in range(t):
+            for k in range(c):
+                out[i, j, k] = tens[i, j, k].reshape(1, ch, 1).clone()
+    return out
+
+
+def write_npz_set(root: str, train, test, code, signature, object_phase: bool = True) -> SynthPaths:
+    """Write the 8 files GestureKNN.sh names.  With object_phase=False the
+    phase column is stored as a dense float32 array (this package reads both;
+    the reference needs the object form)."""
+    os.makedirs(root, exist_ok=True)
+    p = SynthPaths(
+        train_database=os.path.join(root, "train_240_txt_2.npz"),
+        test_data=os.path.join(root, "test_240_txt_2.npz"),
+        train_codebook=os.path.join(root, "train_240_code.npz"),
+        codebook_signature=os.path.join(root, "code.npz"),
+        train_wavlm=os.path.join(root, "train_240_WavLM.npz"),
+        test_wavlm=os.path.join(root, "test_240_WavLM.npz"),
+        train_wavvq=os.path.join(root, "train_240_WavVQ.npz"),
+        test_wavvq=os.path.join(root, "wavvq_240.npz"),
+    )
+    for split, path in ((train, p.train_database), (test, p.test_data)):
+        ph = phase_to_object(split["phase"]) if object_phase else split["phase"]
+        np.savez(path, mfcc=split["mfcc"], energy=split["energy"], pitch=split["pitch"],
+                 volume=split["volume"], phase=ph, context=split["context"])
+    np.savez(p.train_codebook, code=code)
+    np.savez(p.codebook_signature, signature=signature)
+    np.savez(p.train_wavlm, wavlm=train["wavlm"])
+    np.savez(p.test_wavlm, wavlm=test["wavlm"])
+    np.savez(p.train_wavvq, wavvq=train["wavvq"])
+    np.savez(p.test_wavvq, wavvq=test["wavvq"])
+    return p
