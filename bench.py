@@ -1,0 +1,374 @@
+#!/usr/bin/env python
+"""bench.py -- seconds-of-audio matched per second on the phase-guided matcher.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
+line from rank 0.  For N > 1 it is launched under torch.distributed.run, one rank
+per GPU (NCCL).  `--impl reference` times the reference's CPU algorithm (the
+oracle port with the reference's per-window loop) on the host cores instead.
+
+Workload "speaker10_24s" (BASELINE.json configs[2]): synthetic speaker-10-like
+database, N_seq = 512 sequences = 13 312 candidate windows, stacked WavLM
+feature 6 x 1024 = 6144-d + 384-d text context, one 24-s query clip (6 segments
+= 48 query steps) PER GPU.  With N GPUs the database rows are sharded N ways,
+every rank scans its shard for all N clips, the per-shard [48N, 512] tables are
+merged with one NCCL all-gather + a min-merge kernel, and each rank runs the
+sequential tail of its own clip: per-GPU work is constant -> "scaling": "weak".
+
+A step = one pass of the hot path over one batch of clips:
+  value : queries already resident in HBM when the timed region starts
+  e2e   : through CodeKNN.match_clips-equivalent host path, pinned host query
+          buffers -> H2D, kernels, D2H of the int64 codes, all inside the timing
+Inputs (347 MB of windows) are larger than the 126 MB L2 and every pass streams
+all of them, so no explicit L2 flush is needed between iterations.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+SEG_SECONDS = 4.0
+N_SEG = 6  # 24-s clip
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    p.add_argument("--n-seq", type=int, default=512)
+    p.add_argument("--wavlm-dim", type=int, default=1024)
+    p.add_argument("--ctx-dim", type=int, default=384)
+    p.add_argument("--clips-per-gpu", type=int, default=1)
+    p.add_argument("--cpu-sample-seq", type=int, default=32, help="database sequences in the CPU baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--queries-per-pass", type=int, default=0)
+    return p.parse_args()
+
+
+# ------------------------------------------------------------------ synthetic data
+def make_database_arrays(n_seq, wavlm_dim, ctx_dim, seed=0):
+    """Window rows in the layout the matcher scans, from seeded synthetic raw features."""
+    from qpgesture_b200 import data_processing as dp
+    from qpgesture_b200 import synth
+    from qpgesture_b200.matchdb import phase_to_dense
+
+    train, _, code, sig = synth.make_arrays(n_seq, 1, seed=seed, wavlm_dim=wavlm_dim, ctx_dim=ctx_dim)
+    aud_rows = dp.wavlm_window_rows(dp.interpolate_wavlm(train["wavlm"]))
+    txt_rows = np.ascontiguousarray(train["context"].squeeze(2)[:, :26, :].reshape(n_seq * 26, -1))
+    return dict(code=code, signature=sig, phase_amp=phase_to_dense(train["phase"]), aud_rows=aud_rows,
+                txt_rows=txt_rows, train=train)
+
+
+def make_clip_queries(n_clips, wavlm_dim, ctx_dim, seed=1000):
+    from qpgesture_b200 import data_processing as dp
+
+    rng = np.random.default_rng(seed)
+    wav = rng.standard_normal((n_clips * N_SEG, 199, wavlm_dim)).astype(np.float32)
+    ctx = rng.standard_normal((n_clips * N_SEG, 30, ctx_dim)).astype(np.float32)
+    aq = dp.wavlm_query_rows(dp.interpolate_wavlm(wav)).reshape(n_clips, N_SEG, 8, -1)
+    tq = ctx[:, [int(24 * s / 180 * 30) for s in range(8)], :].reshape(n_clips, N_SEG, 8, -1)
+    return np.ascontiguousarray(aq), np.ascontiguousarray(tq), wav, ctx
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = f"/tmp/qpg_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.f = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                         stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        sm, reasons, mx = [], set(), None
+        try:
+            for line in open(self.path):
+                parts = [x.strip() for x in line.split(",")]
+                if len(parts) < 9:
+                    continue
+                sm.append(float(parts[1]))
+                mx = float(parts[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   parts[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.remove(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [x for x in sm if x >= 0.5 * max(sm)] or sm
+            out = {"sm_mhz": statistics.median(busy), "sm_max_mhz": mx, "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------ CPU baseline (oracle port)
+def cpu_baseline(args, n_sample_seq, n_segments=1):
+    """The reference's algorithm with its own cost structure (one scikit-learn call per
+    window and step, single thread) on a bounded sample: `n_sample_seq` database
+    sequences, `n_segments` 4-s segments; cost is linear in the number of sequences
+    (BASELINE.md section 2), so the figure is scaled to args.n_seq."""
+    from oracle import matcher_np as om
+    from qpgesture_b200 import synth
+    from sklearn.metrics.pairwise import paired_distances  # noqa: F401  (import outside the timing)
+
+    train, test, code, sig = synth.make_arrays(n_sample_seq, n_segments, seed=0, wavlm_dim=args.wavlm_dim,
+                                               ctx_dim=args.ctx_dim)
+    db = om.build_db("A", code, sig, train["phase"], train["context"], wavlm=train["wavlm"])
+    aq, tq = om.build_queries("A", test["context"], test_wavlm=test["wavlm"])
+    seed = om.init_code_phase(db, np.random.RandomState(123456))
+    om.scan_loop(db.txt_rows[:26], db.labels[:26], tq[0, 0])          # warm caches / imports
+    t0 = time.perf_counter()
+    om.predict_codes_loop(db, aq, tq, seed)
+    t_loop = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    om.predict_codes(db, aq, tq, seed=seed)
+    t_vec = time.perf_counter() - t0
+    scale = args.n_seq / n_sample_seq
+    audio_s = SEG_SECONDS * n_segments
+    return dict(value=audio_s / (t_loop * scale), unit="s_audio/s", cores=1, kind="port",
+                sample=(f"{n_segments} x 4-s segment against {n_sample_seq} of {args.n_seq} database sequences, "
+                        f"per-window sklearn loop as GestureKNN.py:671-690; {t_loop:.2f} s measured, scaled x{scale:g} "
+                        "(cost linear in sequences)"),
+                vectorised_value=audio_s / (t_vec * scale), host_cores=os.cpu_count())
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    for i in range(args.warmup + args.steps):
+        r = cpu_baseline(args, args.cpu_sample_seq if args.cpu_sample_seq <= 8 else 8, 1)
+        if i >= args.warmup:
+            vals.append(r)
+    v = statistics.mean(x["value"] for x in vals)
+    base = vals[-1]
+    base["value"] = v
+    line = dict(metric="seconds_of_audio_matched_per_second", value=v, unit="s_audio/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * SEG_SECONDS * N_SEG / v,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                impl="reference",
+                config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
+                            audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu),
+                cpu_baseline=base,
+                e2e=dict(value=v, unit="s_audio/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ our arm
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import MatchDatabase, new_table
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    pg = None
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+        pg = dist.group.WORLD
+    lib = _lib.load()
+
+    # ---- database (one-off, outside every timed region)
+    arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
+    j0, j1 = rank * args.n_seq // world, (rank + 1) * args.n_seq // world
+    db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
+                       aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
+    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg)
+    n_clips = args.clips_per_gpu * world
+    aq, tq, _, _ = make_clip_queries(n_clips, args.wavlm_dim, args.ctx_dim)
+    Q = n_clips * N_SEG * 8
+    seed_rng = np.random.RandomState(123456)
+    seeds = []
+    for _ in range(n_clips):
+        i0 = seed_rng.randint(0, args.n_seq)
+        j0_ = seed_rng.randint(0, 180 - 8)
+        seeds.append((int(arrs["code"][i0, j0_ // 30]), arrs["phase_amp"][i0, j0_:j0_ + 8]))
+    seed_code = np.array([s[0] for s in seeds], dtype=np.int32)
+    seed_phase = np.stack([s[1] for s in seeds]).astype(np.float32)
+    my_clips = slice(rank * args.clips_per_gpu, (rank + 1) * args.clips_per_gpu)
+
+    aq_h = torch.from_numpy(aq.reshape(Q, -1)).pin_memory()
+    tq_h = torch.from_numpy(tq.reshape(Q, -1)).pin_memory()
+    aq_d, tq_d = aq_h.to(dev), tq_h.to(dev)
+    codes_h = torch.empty((args.clips_per_gpu, N_SEG, 30), dtype=torch.int64).pin_memory()
+    qpp = args.queries_per_pass
+
+    def scan_and_tail(qa, qt):
+        ta = knn._scan("audio", qa, new_table(Q, dev)) if qpp == 0 else _scan_qpp(knn, "audio", qa, Q, dev, qpp)
+        tt = knn._scan("text", qt, new_table(Q, dev)) if qpp == 0 else _scan_qpp(knn, "text", qt, Q, dev, qpp)
+        # tail of this rank's clips only
+        q0, q1 = my_clips.start * N_SEG * 8, my_clips.stop * N_SEG * 8
+        codes, vote, _, status = knn.tail_device(ta[q0:q1], tt[q0:q1], seed_code[my_clips], seed_phase[my_clips],
+                                                 args.clips_per_gpu, N_SEG, want_phase=False)
+        return codes, status
+
+    def step_resident():
+        return scan_and_tail(aq_d, tq_d)
+
+    def step_e2e():
+        qa = aq_h.to(dev, non_blocking=True)
+        qt = tq_h.to(dev, non_blocking=True)
+        codes, status = scan_and_tail(qa, qt)
+        codes_h.copy_(codes, non_blocking=True)
+        return codes, status
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        l0 = _lib.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count() - l0
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms / steps, launches, out
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, launches, (codes, status) = timed(step_resident, args.steps, args.warmup)
+    ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
+    assert int(status.max().cpu()) == 0, "tail reported a start-code without window"
+
+    # ---- dominant kernel alone: one audio pass (one launch) at the library's queries-per-pass
+    qpp_used = 4 if 6 * args.wavlm_dim > 2048 else 8
+    qa_small = aq_d[:qpp_used].contiguous()
+    tab_small = new_table(qpp_used, dev)
+    t = db.aud
+    sp = _lib.stream_ptr()
+
+    def one_pass():
+        _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W, t.D,
+                                                 db.id_offset, _lib.ptr(qa_small), qpp_used, _lib.ptr(tab_small),
+                                                 qpp_used, sp), "cosine")
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab_small), qpp_used * 512, sp), "init")
+    for _ in range(5):
+        one_pass()
+    torch.cuda.synchronize()
+    reps = 50
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        one_pass()
+    e1.record()
+    torch.cuda.synchronize()
+    pass_ms = e0.elapsed_time(e1) / reps
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        alg_bytes = db.algorithmic_bytes("audio")
+        achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
+        audio_seconds = n_clips * N_SEG * SEG_SECONDS
+        line = dict(
+            metric="seconds_of_audio_matched_per_second", value=audio_seconds / (ms_res * 1e-3), unit="s_audio/s",
+            n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
+            scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
+                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu,
+                        query_steps_per_step=Q, db_bytes=int(db.aud.nbytes + db.txt.nbytes) * world,
+                        parallelism=f"rows sharded x{world}, all-gather + min-merge" if world > 1 else "single GPU",
+                        l2="inputs larger than L2 (no flush needed)" if db.aud.nbytes > 126e6 else
+                           "database shard fits L2; passes re-read it from L2"),
+            e2e=dict(value=audio_seconds / (ms_e2e * 1e-3), unit="s_audio/s", ms_per_step=ms_e2e,
+                     h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4),
+                     d2h_bytes_per_step=int(codes_h.numel() * 8)),
+            gpu_launches=int(launches),
+            roofline=dict(bound="hbm", kernel=f"cand_cosine_kernel<QT={qpp_used}>", achieved=achieved, peak=peak,
+                          unit="GB/s", frac=achieved / peak, traffic=None, launch_ms=pass_ms,
+                          algorithmic_bytes=int(alg_bytes),
+                          peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"),
+            clocks=clocks,
+        )
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def _scan_qpp(knn, which, q, Q, dev, qpp):
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import new_table
+
+    lib, db = _lib.load(), knn.db
+    table = new_table(Q, dev)
+    sp = _lib.stream_ptr()
+    t = db.txt if which == "text" else db.aud
+    _lib.check(lib.qpg_table_init(_lib.ptr(table), Q * 512, sp), "init")
+    _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W, t.D,
+                                             db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), qpp, sp), "cosine")
+    if knn.process_group is not None:
+        table = knn._merge_shards(table)
+    return table
+
+
+if __name__ == "__main__":
+    main()

@@ -54,6 +54,8 @@ int qpg_version(void);
 const char* qpg_last_error(void);
 /* number of kernels this library has launched in the calling process */
 uint64_t qpg_launch_count(void);
+/* tuning hook for sweeps (0 = automatic): compute warps per CTA (8|12), ring depth, grid size */
+int qpg_tune_cosine(int compute_warps, int stages, int grid);
 
 /* ---------------- packed window database ---------------------------------
  * Row-major float32 windows [W, D] are re-laid-out once per database into

@@ -1,0 +1,286 @@
+"""Parity of the CUDA matcher (through the C ABI) against the oracle and the
+golden vectors produced by the reference.  All tests need a GPU."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from oracle import matcher_np as om
+from tests._common import golden_cases, load_case, oracle_db, oracle_queries
+
+pytestmark = pytest.mark.gpu
+
+CASES = golden_cases()
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _scan_cosine(rows, labels, q, id_offset=0, qpp=0):
+    """rows [W,D] f32, labels [W] -> numpy structured table [Q,512] via the C ABI."""
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import PackedRows, new_table, table_to_numpy
+
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    pr = PackedRows.from_rows(torch.from_numpy(np.ascontiguousarray(rows, dtype=np.float32)).to(dev))
+    lab = torch.from_numpy(np.ascontiguousarray(labels, dtype=np.int32)).to(dev)
+    qd = torch.from_numpy(np.ascontiguousarray(q, dtype=np.float32)).to(dev)
+    tab = new_table(qd.shape[0], dev)
+    sp = _lib.stream_ptr()
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab), tab.shape[0] * 512, sp), "init")
+    _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(pr.packed), _lib.ptr(pr.sqnorm), _lib.ptr(lab), pr.W, pr.D,
+                                             id_offset, _lib.ptr(qd), qd.shape[0], _lib.ptr(tab), qpp, sp), "cos")
+    torch.cuda.synchronize()
+    return table_to_numpy(tab), pr
+
+
+def _oracle_cosine_table(rows, labels, q):
+    d = om.cosine_rows(np.asarray(q, dtype=np.float64), np.asarray(rows, dtype=np.float64))
+    return om.min_by_code(d, np.asarray(labels, dtype=np.int64)), d
+
+
+@pytest.mark.parametrize("W,D,Q", [(1000, 384, 3), (777, 512, 8), (130, 200, 1), (2048, 6144, 5), (9, 128, 11),
+                                   (5000, 512, 2), (64, 1024, 4)])
+def test_cosine_minbycode_vs_oracle(W, D, Q):
+    rng = np.random.default_rng(W * 7 + D)
+    rows = rng.standard_normal((W, D)).astype(np.float32)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    labels = rng.integers(0, 300, size=W)                    # bins 300..511 stay empty
+    if W > 20:
+        rows[11] = rows[3]                                   # exact duplicate: the smaller id must win
+        labels[11] = labels[3]
+        rows[17] = 0.0                                       # all-zero window (sklearn: norm 0 -> 1)
+        q[0] = rows[5]                                       # query equal to a window
+    table, pr = _scan_cosine(rows, labels, q)
+    sq = pr.sqnorm.cpu().numpy()
+    assert np.allclose(sq, (rows.astype(np.float64) ** 2).sum(1), rtol=1e-14, atol=0)
+    for qi in range(Q):
+        (bd, bw), d_all = _oracle_cosine_table(rows, labels, q[qi])
+        assert np.array_equal(table[qi]["id"], bw), f"window ids differ for query {qi}"
+        assert np.allclose(table[qi]["d"], bd, rtol=0, atol=1e-12)
+        assert np.all(table[qi]["d"][bw < 0] == 1e3)
+
+
+def test_cosine_queries_per_pass_and_offset():
+    rng = np.random.default_rng(5)
+    W, D, Q = 1500, 384, 7
+    rows = rng.standard_normal((W, D)).astype(np.float32)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    labels = rng.integers(0, 512, size=W)
+    base, _ = _scan_cosine(rows, labels, q)
+    for qpp in (1, 2, 4, 8):
+        t, _ = _scan_cosine(rows, labels, q, qpp=qpp)
+        assert np.array_equal(t["id"], base["id"]) and np.array_equal(t["d"], base["d"])
+    off, _ = _scan_cosine(rows, labels, q, id_offset=26 * 1000)
+    assert np.array_equal(off["id"][base["id"] >= 0], base["id"][base["id"] >= 0] + 26000)
+
+
+def test_sharded_scan_merges_to_full():
+    """Row shards scanned into separate tables + qpg_table_merge == one full scan."""
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import new_table, table_to_numpy
+
+    rng = np.random.default_rng(9)
+    W, D, Q = 26 * 40, 256, 6
+    rows = rng.standard_normal((W, D)).astype(np.float32)
+    rows[26 * 30 + 2] = rows[4]                               # tie across shards: global id 4 must win
+    labels = rng.integers(0, 100, size=W)
+    labels[26 * 30 + 2] = labels[4]
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    full, _ = _scan_cosine(rows, labels, q)
+    cuts = [0, 26 * 7, 26 * 19, 26 * 30, W]
+    parts = [_scan_cosine(rows[a:b], labels[a:b], q, id_offset=a)[0] for a, b in zip(cuts[:-1], cuts[1:])]
+    stacked = np.stack(parts)                                 # [P,Q,512] structured
+    dev = torch.device("cuda")
+    pt = torch.from_numpy(stacked.view(np.int64).reshape(len(parts), Q, 512, 2).copy()).to(dev)
+    out = new_table(Q, dev)
+    lib = _lib.load()
+    _lib.check(lib.qpg_table_merge(_lib.ptr(pt), len(parts), Q * 512, _lib.ptr(out), _lib.stream_ptr()), "merge")
+    merged = table_to_numpy(out)
+    assert np.array_equal(merged["id"], full["id"]) and np.array_equal(merged["d"], full["d"])
+
+
+@pytest.mark.parametrize("W,Q,alphabet", [(3000, 9, 4), (500, 4, 50), (26 * 64, 8, 102400), (7, 1, 3)])
+def test_levenshtein_minbycode_vs_oracle(W, Q, alphabet):
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import new_table, pad_tokens, table_to_numpy
+
+    rng = np.random.default_rng(W + Q)
+    tok = rng.integers(0, alphabet, size=(W, 11))
+    qt = rng.integers(0, alphabet, size=(Q, 11))
+    qt[0] = tok[W // 2]
+    labels = rng.integers(0, 512, size=W)
+    dev = torch.device("cuda")
+    lib = _lib.load()
+    t_d = torch.from_numpy(pad_tokens(tok).view(np.int32)).to(dev)
+    q_d = torch.from_numpy(pad_tokens(qt).view(np.int32)).to(dev)
+    lab = torch.from_numpy(labels.astype(np.int32)).to(dev)
+    tab = new_table(Q, dev)
+    sp = _lib.stream_ptr()
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab), Q * 512, sp), "init")
+    _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(t_d), _lib.ptr(lab), W, 0, _lib.ptr(q_d), Q, _lib.ptr(tab), sp), "lev")
+    got = table_to_numpy(tab)
+    for qi in range(Q):
+        d = om.levenshtein_rows(qt[qi], tok).astype(np.float64)
+        bd, bw = om.min_by_code(d, labels)
+        assert np.array_equal(got[qi]["id"], bw)
+        assert np.array_equal(got[qi]["d"], bd)                # exact integers
+    # plain pairwise distances (wavvq_distances 'combine')
+    out = torch.empty(W, dtype=torch.int32, device=dev)
+    qrep = torch.from_numpy(pad_tokens(np.repeat(qt[:1], W, 0)).view(np.int32)).to(dev)
+    _lib.check(lib.qpg_lev_distance(_lib.ptr(qrep), _lib.ptr(t_d), W, _lib.ptr(out), sp), "levd")
+    assert np.array_equal(out.cpu().numpy(), om.levenshtein_rows(qt[0], tok))
+
+
+def test_wavvq_distances_api():
+    from qpgesture_b200.GestureKNN import wavvq_distances
+
+    rng = np.random.default_rng(1)
+    a = rng.integers(0, 320, size=22).astype(np.float64)
+    b = a.copy()
+    b[[0, 1, 8, 9]] = [5, 6, 7, 8]
+    ta, tb = om.wavvq_tokens(a), om.wavvq_tokens(b)
+    assert wavvq_distances(a, b, mode="combine") == int(om.levenshtein_rows(ta, tb[None])[0])
+    assert wavvq_distances(a, a, mode="combine") == 0
+
+
+def test_rank512_stable():
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import PAIR_DTYPE
+
+    rng = np.random.default_rng(3)
+    Q = 5
+    tab = np.zeros((Q, 512), dtype=PAIR_DTYPE)
+    tab["d"] = rng.integers(0, 12, size=(Q, 512)).astype(np.float64)   # heavy ties
+    tab["d"][1] = rng.random(512)
+    tab["d"][2, 100:] = 1e3
+    tab["id"] = 1
+    dev = torch.device("cuda")
+    t = torch.from_numpy(tab.view(np.int64).reshape(Q, 512, 2).copy()).to(dev)
+    r = torch.empty((Q, 512), dtype=torch.int32, device=dev)
+    lib = _lib.load()
+    _lib.check(lib.qpg_rank512(_lib.ptr(t), Q, _lib.ptr(r), _lib.stream_ptr()), "rank")
+    want = np.stack([tab["d"][i].argsort(kind="stable").argsort(kind="stable") for i in range(Q)])
+    assert np.array_equal(r.cpu().numpy(), want)
+
+
+def _knn_from_case(mode, train, code, sig, fx, tail):
+    from qpgesture_b200 import data_processing as dp
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import MatchDatabase, mode_b_window_frames, phase_to_dense, wavvq_tokens
+
+    n = code.shape[0]
+    txt_rows = train["context"].squeeze(2)[:, :26, :].reshape(n * 26, -1)
+    kw = {}
+    if mode == "A":
+        kw["aud_rows"] = dp.wavlm_window_rows(dp.interpolate_wavlm(train["wavlm"]))
+    else:
+        ks, _ = mode_b_window_frames()
+        kw["aud_tokens"] = wavvq_tokens(dp.stack_wavvq_feat(train["wavvq"])[:, ks, :]).reshape(n * 26, -1)
+    db = MatchDatabase(mode, code, sig, phase_to_dense(train["phase"]), txt_rows, freq_rank=fx["freq_rank"], **kw)
+    return CodeKNN(database=db, use_wavlm=mode == "A", use_wavvq=mode == "B", use_phase=True, use_txt=True, tail=tail)
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_golden_tables_mode_a(path):
+    """search_audio_cands / search_text_cands against the reference's recorded outputs."""
+    from qpgesture_b200 import data_processing as dp
+
+    fx, train, test, code, sig = load_case(path)
+    knn = _knn_from_case("A", train, code, sig, fx, "device")
+    aq = dp.wavlm_query_rows(dp.interpolate_wavlm(test["wavlm"]))
+    ctx = test["context"].squeeze(2)
+    for s in range(8):
+        d, idx, aux = knn.search_audio_cands(aq[0, s], mode="wavlm_feat")
+        w = np.array([-1 if len(a) == 0 else 26 * a[0] + a[1] // 6 for a in aux])
+        assert np.array_equal(w, fx["aud_w"][s])
+        assert np.allclose(d, fx["aud_d"][s], rtol=0, atol=1e-12)
+        for c in range(512):
+            if w[c] >= 0:
+                j, m = divmod(int(w[c]), 26)
+                assert np.array_equal(idx[c], code[j, m:m + 4])
+        d, idx, aux = knn.search_text_cands(ctx[0, int(24 * s / 180 * 30)])
+        w = np.array([-1 if len(a) == 0 else 26 * a[0] + a[1] // 8 for a in aux])
+        # reference text distances are float32 sklearn arithmetic; ours float64 on the same data
+        mism = np.flatnonzero(w != fx["txt_w"][s])
+        assert len(mism) == 0, f"text windows differ in bins {mism}"
+        assert np.allclose(d, fx["txt_d"][s], rtol=0, atol=5e-7)
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_golden_tables_mode_b(path):
+    from qpgesture_b200 import data_processing as dp
+
+    fx, train, test, code, sig = load_case(path)
+    knn = _knn_from_case("B", train, code, sig, fx, "device")
+    vq = dp.stack_wavvq_feat(test["wavvq"])
+    step, i = 4 * (398 / 30), 0
+    for s in range(8):
+        d, idx, aux = knn.search_audio_cands(vq[0, int(i)], mode="wavvq_feat")
+        ks, _ = om.mode_b_window_k()
+        kmap = {int(k): m for m, k in enumerate(ks)}
+        w = np.array([-1 if len(a) == 0 else 26 * a[0] + kmap[a[1]] for a in aux])
+        assert np.array_equal(w, fx["lev_w"][s])
+        assert np.array_equal(np.array(d), fx["lev_d"][s])
+        i += step
+
+
+@pytest.mark.parametrize("tail", ["device", "numpy"])
+@pytest.mark.parametrize("path", CASES)
+def test_golden_end_to_end_mode_a(path, tail):
+    """knn_pred of the reference's main_codebook, reproduced by match_clips."""
+    from qpgesture_b200 import data_processing as dp
+
+    fx, train, test, code, sig = load_case(path)
+    knn = _knn_from_case("A", train, code, sig, fx, tail)
+    aq = dp.wavlm_query_rows(dp.interpolate_wavlm(test["wavlm"]))
+    ctx = test["context"].squeeze(2)
+    tq = ctx[:, [int(24 * s / 180 * 30) for s in range(8)], :]
+    np.random.seed(123456)
+    got = knn.match_clips(aq[None], tq[None], tail=tail)[0]
+    assert np.array_equal(got, fx["knn_pred"])
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_device_tail_vs_oracle_stable(path):
+    """Device tail == oracle tail with stable tie order, given the same tables."""
+    from qpgesture_b200 import data_processing as dp
+
+    fx, train, test, code, sig = load_case(path)
+    knn = _knn_from_case("A", train, code, sig, fx, "device")
+    db = oracle_db("A", train, code, sig)
+    aq, tq = oracle_queries("A", test)
+    want = om.predict_codes(db, aq, tq, ties="stable", freq_score=fx["freq_rank"],
+                            seed=(int(fx["init_code"]), fx["init_phase"]))
+    got = knn.match_clips(aq[None].astype(np.float32), tq[None], seed_code=[int(fx["init_code"])],
+                          seed_phase=fx["init_phase"][None], tail="device")[0]
+    assert np.array_equal(got, want)
+
+
+def test_cli_end_to_end_files():
+    """GestureKNN.main on npz files in the reference's formats (dense phase) vs the oracle."""
+    from qpgesture_b200 import GestureKNN as G
+    from qpgesture_b200 import synth
+    from qpgesture_b200.matchdb import freq_rank_from_code
+
+    train, test, code, sig = synth.make_arrays(48, 3, seed=11, wavlm_dim=32, ctx_dim=48)
+    with tempfile.TemporaryDirectory() as root:
+        p = synth.write_npz_set(root, train, test, code, sig, object_phase=False)
+        out = os.path.join(root, "o", "result.npz")
+        got = G.main(p.as_argv(out, max_frames=0) + ["--tail", "numpy"])
+        assert np.array_equal(np.load(out)["knn_pred"], got)
+    db = oracle_db("A", train, code, sig)
+    aq, tq = oracle_queries("A", test)
+    np.random.seed(123456)
+    rep = []
+    want = om.predict_codes(db, aq, tq, ties="numpy", freq_score=freq_rank_from_code(code), report=rep)
+    assert got.shape == (3, 30) and got.dtype == np.int64
+    assert np.array_equal(got, want)
