@@ -125,33 +125,13 @@ __global__ void __launch_bounds__(NCW * 32, 1)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nthreads = NCW * 32;
 
-  // ---- prologue: queries, table, barriers
-  for (int i = tid; i < QT * Dp; i += nthreads) {
-    const int qi = i / Dp, d = i - qi * Dp;
-    qs[i] = (qi < nq && d < D) ? q[(size_t)qi * D + d] : 0.f;
-  }
-  for (int i = tid; i < QT * KB; i += nthreads) {
-    Pair p;
-    p.d = (unsigned long long)__double_as_longlong(kEmptyDist);
-    p.id = ~0ull;
-    tab[i] = p;
-  }
+  // ---- prologue: barriers, queries (one TMA bulk copy when rows are unpadded), table
+  uint64_t* qbar = bars + NCW * NS;
   if (tid < NCW * NS) mbar_init(&bars[tid], 1);
+  if (tid == 0) mbar_init(qbar, 1);
   fence_mbar_init();
   __syncthreads();
-  if (warp < QT) {
-    double s = 0.0;
-    for (int d = lane; d < Dp; d += 32) {
-      const double v = (double)qs[warp * Dp + d];
-      s = fma(v, v, s);
-    }
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) qn[warp] = s;
-  }
-  __syncthreads();
-
-  // ---- this warp's contiguous run of row groups
+  // ---- this warp's contiguous run of row groups; its first tiles start flowing before the queries land
   const int64_t slot = (int64_t)blockIdx.x * NCW + warp;
   const int64_t nslots = (int64_t)gridDim.x * NCW;
   const int64_t g0 = slot * G / nslots, g1 = (slot + 1) * G / nslots;
@@ -166,6 +146,40 @@ __global__ void __launch_bounds__(NCW * 32, 1)
       bulk_g2s(my_ring + (size_t)s * TILE_FLOATS, stream + (int64_t)s * TILE_FLOATS, TILE_BYTES, &my_bars[s]);
     }
   }
+
+  const bool q_bulk = (D == Dp) && ((reinterpret_cast<uintptr_t>(q) & 15) == 0);
+  if (q_bulk) {
+    if (tid == 0) {
+      const uint32_t bytes = (uint32_t)nq * (uint32_t)Dp * 4u;
+      mbar_arrive_expect_tx(qbar, bytes);
+      bulk_g2s(qs, q, bytes, qbar);
+    }
+    for (int i = nq * Dp + tid; i < QT * Dp; i += nthreads) qs[i] = 0.f;
+  } else {
+    for (int i = tid; i < QT * Dp; i += nthreads) {
+      const int qi = i / Dp, d = i - qi * Dp;
+      qs[i] = (qi < nq && d < D) ? q[(size_t)qi * D + d] : 0.f;
+    }
+  }
+  for (int i = tid; i < QT * KB; i += nthreads) {
+    Pair p;
+    p.d = (unsigned long long)__double_as_longlong(kEmptyDist);
+    p.id = ~0ull;
+    tab[i] = p;
+  }
+  if (q_bulk) mbar_wait(qbar, 0);
+  __syncthreads();
+  if (warp < QT) {
+    double s = 0.0;
+    for (int d = lane; d < Dp; d += 32) {
+      const double v = (double)qs[warp * Dp + d];
+      s = fma(v, v, s);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) qn[warp] = s;
+  }
+  __syncthreads();
 
   double acc[R * QT];
 #pragma unroll
@@ -267,7 +281,7 @@ int launch_cosine(const float* packed, const double* row_sqnorm, const int32_t* 
   const int NC = (D + DC - 1) / DC;
   const int64_t G = (W + R - 1) / R;
   const size_t smem = (size_t)NCW * NS * TILE_BYTES + (size_t)QT * NC * DC * 4 + (size_t)QT * KB * sizeof(Pair) +
-                      8 * sizeof(double) + (size_t)NCW * NS * sizeof(uint64_t);
+                      8 * sizeof(double) + ((size_t)NCW * NS + 1) * sizeof(uint64_t);
   auto kern = cand_cosine_kernel<QT, NCW>;
   QPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NCW * 32, smem, st>>>(packed, row_sqnorm, labels, W, D, NC, G, id_offset, q, nq, table, NS);
@@ -345,11 +359,11 @@ extern "C" int qpg_cand_cosine_minbycode(const float* packed, const double* row_
     return QPG_E_UNSUPPORTED;
   }
   const int tiles_fit = (int)((kSmemLimit - fixed_smem(qt, D)) / TILE_BYTES);
-  int ncw = g_tuning.ncw ? g_tuning.ncw : (qt == 8 ? 8 : (tiles_fit >= 36 ? 12 : 8));
+  int ncw = g_tuning.ncw ? g_tuning.ncw : (qt == 8 ? 8 : (tiles_fit >= 24 ? 12 : 8));
   if (qt == 8) ncw = 8;
   if (ncw != 8 && ncw != 12) ncw = 8;
   int ns = g_tuning.ns ? g_tuning.ns : tiles_fit / ncw;
-  if (ns > 4) ns = 4;
+  if (ns > 3) ns = 3;
   if (ns * ncw > tiles_fit) ns = tiles_fit / ncw;
   if (ns < 1) {
     set_error("no room for a tile ring (D=%d)", D);
