@@ -217,7 +217,8 @@ def main():
 
     # ---- database (one-off, outside every timed region)
     arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
-    j0, j1 = rank * args.n_seq // world, (rank + 1) * args.n_seq // world
+    from qpgesture_b200.sharding import shard_sequences
+    j0, j1 = shard_sequences(args.n_seq, world, rank)
     db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
                        aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
     knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg)

@@ -1,0 +1,278 @@
+"""B200 drop-in for the inference surface of the reference VQ-VAE
+(codebook/models/vqvae.py, bottleneck.py, encdec.py, resnet.py).
+
+Same class and method names and argument meaning -- `VQVAE(hps, input_dim)`
+with `.encode(x) -> [LongTensor]`, `.decode(zs) -> Tensor[B,T,C]`,
+`.load_state_dict` accepting the reference's checkpoint keys (with or without
+the DataParallel 'module.' prefix), `BottleneckBlock.quantise / dequantise /
+encode / decode`, `Encoder`, `Decoder` -- but activations stay channels-last
+[B, T, C] on the GPU end to end (no NCT<->NTC permutes) and every
+layer is a launch of libqpg_sm100.so's tap-GEMM (qpg_conv1d_taps_f32), the
+transposed convolutions as two sub-pixel phases; the quantiser is the fused
+L2-argmin kernel (no [N*T', 512] distance matrix in memory).
+
+Training (`forward` losses, EMA codebook updates: vqvae.py:187-303,
+bottleneck.py:39-94) is out of scope and raises.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _strip_module(sd):
+    return {(k[7:] if k.startswith("module.") else k): v for k, v in sd.items()}
+
+
+class _TapConv:
+    """One launch of qpg_conv1d_taps_f32: weights packed [n_taps, C_in, C_out]."""
+
+    def __init__(self, w_taps: torch.Tensor, bias: Optional[torch.Tensor], tap_offset, in_stride=1, out_stride=1,
+                 out_offset=0, relu_in=False, precision=0):
+        self.w = w_taps.contiguous()
+        self.bias = None if bias is None else bias.contiguous()
+        self.n_taps, self.c_in, self.c_out = self.w.shape
+        self.tap_offset = list(tap_offset)
+        self.in_stride, self.out_stride, self.out_offset = in_stride, out_stride, out_offset
+        self.relu_in = bool(relu_in)
+        self.precision = precision
+
+    def __call__(self, x: torch.Tensor, out: torch.Tensor, n_out: int, residual: Optional[torch.Tensor] = None):
+        lib = _lib.load()
+        B, T_in, C = x.shape
+        assert C == self.c_in and out.shape[0] == B and out.shape[2] == self.c_out
+        d = _lib.ConvDesc()
+        d.B, d.T_in, d.T_out_total, d.C_in, d.C_out = B, T_in, out.shape[1], self.c_in, self.c_out
+        d.n_taps = self.n_taps
+        for i in range(4):
+            d.tap_offset[i] = self.tap_offset[i] if i < self.n_taps else 0
+        d.in_stride, d.out_stride, d.out_offset, d.n_out = self.in_stride, self.out_stride, self.out_offset, n_out
+        d.relu_in, d.precision = int(self.relu_in), self.precision
+        _lib.check(lib.qpg_conv1d_taps_f32(d, _lib.ptr(x), _lib.ptr(self.w), _lib.ptr(self.bias), _lib.ptr(residual),
+                                           _lib.ptr(out), _lib.stream_ptr()), "qpg_conv1d_taps_f32")
+        return out
+
+
+def _pack_conv(weight: torch.Tensor) -> torch.Tensor:
+    """nn.Conv1d weight [C_out, C_in, k] -> [k, C_in, C_out]."""
+    return weight.permute(2, 1, 0).contiguous()
+
+
+def _pack_convT(weight: torch.Tensor, taps) -> torch.Tensor:
+    """nn.ConvTranspose1d weight [C_in, C_out, k] -> [len(taps), C_in, C_out] for the chosen k's."""
+    return torch.stack([weight[:, :, k] for k in taps]).contiguous()
+
+
+class ResConv1DBlock:
+    """x + conv1(relu(conv3_dilated(relu(x))))  (resnet.py:27-46)."""
+
+    def __init__(self, sd, prefix, dilation, device, precision=0):
+        g = lambda n: sd[prefix + n].to(device=device, dtype=torch.float32)
+        self.conv3 = _TapConv(_pack_conv(g(".1.weight")), g(".1.bias"), [-dilation, 0, dilation], relu_in=True,
+                              precision=precision)
+        self.conv1 = _TapConv(_pack_conv(g(".3.weight")), g(".3.bias"), [0], relu_in=True, precision=precision)
+
+    def __call__(self, x, tmp, out):
+        T = x.shape[1]
+        self.conv3(x, tmp, T)
+        self.conv1(tmp, out, T, residual=x)
+        return out
+
+
+class Resnet1D:
+    """depth ResConv1DBlocks, dilations growth**d, reversed in the decoder (resnet.py:48-77)."""
+
+    def __init__(self, sd, prefix, depth, growth, reverse, device, precision=0):
+        dil = [growth ** d for d in range(depth)]
+        if reverse:
+            dil = dil[::-1]
+        self.blocks = [ResConv1DBlock(sd, f"{prefix}.model.{d}.model", dil[d], device, precision) for d in range(depth)]
+
+    def __call__(self, x):
+        tmp = torch.empty_like(x)
+        for blk in self.blocks:
+            out = torch.empty_like(x)
+            x = blk(x, tmp, out)
+        return x
+
+
+class Encoder:
+    """encdec.py:8-30,53-90 for one level: down_t x (Conv1d k=2s, stride s, pad s/2 -> Resnet1D) -> Conv1d k3."""
+
+    def __init__(self, sd, hps, device, precision=0):
+        down_t, s = hps.downs_t[0], hps.strides_t[0]
+        assert s == 2, "stride 2 is what the reference config uses (codebook.yml:4)"
+        pre = "encoders.0.level_blocks.0.model"
+        g = lambda n: sd[n].to(device=device, dtype=torch.float32)
+        self.downs, self.res = [], []
+        for i in range(down_t):
+            k = 2 * s
+            offs = [j - s // 2 for j in range(k)]                       # t_in = s*t - pad + j
+            self.downs.append(_TapConv(_pack_conv(g(f"{pre}.{i}.0.weight")), g(f"{pre}.{i}.0.bias"), offs, in_stride=s,
+                                       precision=precision))
+            self.res.append(Resnet1D(sd, f"{pre}.{i}.1", hps.depth, hps.dilation_growth_rate, False, device, precision))
+        self.out = _TapConv(_pack_conv(g(f"{pre}.{down_t}.weight")), g(f"{pre}.{down_t}.bias"), [-1, 0, 1],
+                            precision=precision)
+        self.stride = s
+
+    def __call__(self, x):                                              # x [B, T, C_in] float32
+        for down, res in zip(self.downs, self.res):
+            B, T, _ = x.shape
+            assert T % self.stride == 0, "sequence length must be divisible by the total stride"
+            y = torch.empty((B, T // self.stride, down.c_out), dtype=torch.float32, device=x.device)
+            x = res(down(x, y, T // self.stride))
+        y = torch.empty((x.shape[0], x.shape[1], self.out.c_out), dtype=torch.float32, device=x.device)
+        return self.out(x, y, x.shape[1])
+
+
+class Decoder:
+    """encdec.py:32-51,92-136: Conv1d k3 -> down_t x (Resnet1D reversed -> ConvTranspose1d k4 s2 p1) -> out Conv1d k3."""
+
+    def __init__(self, sd, hps, device, precision=0):
+        down_t, s = hps.downs_t[0], hps.strides_t[0]
+        assert s == 2
+        pre = "decoders.0.level_blocks.0.model"
+        g = lambda n: sd[n].to(device=device, dtype=torch.float32)
+        self.inp = _TapConv(_pack_conv(g(f"{pre}.0.weight")), g(f"{pre}.0.bias"), [-1, 0, 1], precision=precision)
+        self.res, self.up_even, self.up_odd = [], [], []
+        for i in range(down_t):
+            self.res.append(Resnet1D(sd, f"{pre}.{i + 1}.0", hps.depth, hps.dilation_growth_rate,
+                                     hps.vqvae_reverse_decoder_dilation, device, precision))
+            w, b = g(f"{pre}.{i + 1}.1.weight"), g(f"{pre}.{i + 1}.1.bias")
+            # t_out = 2*t_in - 1 + k :  even t_out=2u <- (k=1,t_in=u),(k=3,t_in=u-1) ; odd 2u+1 <- (k=0,u+1),(k=2,u)
+            self.up_even.append(_TapConv(_pack_convT(w, (1, 3)), b, [0, -1], out_stride=2, out_offset=0,
+                                         precision=precision))
+            self.up_odd.append(_TapConv(_pack_convT(w, (0, 2)), b, [1, 0], out_stride=2, out_offset=1,
+                                        precision=precision))
+        self.out = _TapConv(_pack_conv(g("decoders.0.out.weight")), g("decoders.0.out.bias"), [-1, 0, 1],
+                            precision=precision)
+
+    def __call__(self, x):                                              # x [B, T', emb]
+        y = torch.empty((x.shape[0], x.shape[1], self.inp.c_out), dtype=torch.float32, device=x.device)
+        x = self.inp(x, y, x.shape[1])
+        for res, ue, uo in zip(self.res, self.up_even, self.up_odd):
+            x = res(x)
+            B, T, _ = x.shape
+            y = torch.empty((B, 2 * T, ue.c_out), dtype=torch.float32, device=x.device)
+            ue(x, y, T)
+            uo(x, y, T)
+            x = y
+        y = torch.empty((x.shape[0], x.shape[1], self.out.c_out), dtype=torch.float32, device=x.device)
+        return self.out(x, y, x.shape[1])
+
+
+class BottleneckBlock:
+    """Inference half of bottleneck.py:15-154 (quantise / dequantise / encode / decode)."""
+
+    def __init__(self, k_bins, emb_width, mu=0.99, device=None):
+        self.k_bins, self.emb_width, self.mu = k_bins, emb_width, mu
+        self.device = torch.device(device if device is not None else "cuda")
+        self.k = torch.zeros((k_bins, emb_width), dtype=torch.float32, device=self.device)   # bottleneck.py:28
+
+    def quantise(self, x):
+        """x [M, emb] float32 (device) -> (x_l int64 [M], fit scalar)  (bottleneck.py:120-126)."""
+        lib = _lib.load()
+        x = x.contiguous()
+        M = x.shape[0]
+        x_l = torch.empty((M,), dtype=torch.int64, device=x.device)
+        mind = torch.empty((M,), dtype=torch.float32, device=x.device)
+        _lib.check(lib.qpg_vq_argmin_f32(_lib.ptr(x), _lib.ptr(self.k), M, self.emb_width, self.k_bins, _lib.ptr(x_l),
+                                         _lib.ptr(mind), _lib.stream_ptr()), "qpg_vq_argmin_f32")
+        return x_l, torch.mean(mind)
+
+    def dequantise(self, x_l):
+        """int64 [...] -> float32 [..., emb]  (F.embedding, bottleneck.py:128-130)."""
+        lib = _lib.load()
+        flat = x_l.reshape(-1).contiguous()
+        out = torch.empty((flat.shape[0], self.emb_width), dtype=torch.float32, device=flat.device)
+        _lib.check(lib.qpg_vq_dequantise_f32(_lib.ptr(flat), _lib.ptr(self.k), flat.shape[0], self.emb_width,
+                                             self.k_bins, _lib.ptr(out), _lib.stream_ptr()), "qpg_vq_dequantise_f32")
+        return out.view(tuple(x_l.shape) + (self.emb_width,))
+
+    def encode(self, x_btc):
+        """channels-last latents [N, T', emb] -> codes [N, T']  (bottleneck.py:132-143)."""
+        N, T, C = x_btc.shape
+        x_l, _ = self.quantise(x_btc.reshape(N * T, C))
+        return x_l.view(N, T)
+
+    def decode(self, x_l):
+        """codes [N, T'] -> channels-last [N, T', emb]  (bottleneck.py:145-154, without the NCT permute)."""
+        return self.dequantise(x_l)
+
+
+class VQVAE:
+    """Inference surface of models/vqvae.py:52-181 (levels = 1)."""
+
+    def __init__(self, hps, input_dim=72, device=None, precision=0):
+        assert hps.levels == 1, "the reference config uses one level (codebook.yml:3)"
+        _lib.load()
+        self.hps = hps
+        self.input_dim = input_dim
+        self.device = torch.device(device if device is not None else "cuda")
+        self.precision = precision
+        self.levels = 1
+        self.l_bins = hps.l_bins
+        self.encoder: Optional[Encoder] = None
+        self.decoder: Optional[Decoder] = None
+        self.bottleneck = BottleneckBlock(hps.l_bins, hps.emb_width, hps.l_mu, self.device)
+        self.hop = int(np.prod([s ** d for s, d in zip(hps.strides_t, hps.downs_t)]))
+
+    # -- checkpoint ------------------------------------------------------------------
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        sd = _strip_module(state_dict)
+        self.encoder = Encoder(sd, self.hps, self.device, self.precision)
+        self.decoder = Decoder(sd, self.hps, self.device, self.precision)
+        self.bottleneck.k = sd["bottleneck.level_blocks.0.k"].to(device=self.device, dtype=torch.float32).contiguous()
+        return self
+
+    def eval(self):
+        return self
+
+    def to(self, device):
+        assert torch.device(device).type == "cuda", "there is no CPU path"
+        return self
+
+    # -- inference ---------------------------------------------------------------------
+    def preprocess(self, x):
+        assert len(x.shape) == 3
+        return x.to(device=self.device, dtype=torch.float32).contiguous()          # stays NTC (vqvae.py:127-131)
+
+    def latents(self, x):
+        with torch.cuda.device(self.device):
+            return self.encoder(self.preprocess(x))
+
+    def _encode(self, x, start_level=0, end_level=None):
+        with torch.cuda.device(self.device):
+            h = self.encoder(self.preprocess(x))
+            return [self.bottleneck.encode(h)][start_level:end_level]
+
+    def encode(self, x, start_level=0, end_level=None, bs_chunks=1):
+        """x [B, T, C] -> [LongTensor [B, T/8]]  (vqvae.py:174-181)."""
+        x = torch.as_tensor(x)
+        outs = [self._encode(xi, start_level, end_level) for xi in torch.chunk(x, bs_chunks, dim=0)]
+        return [torch.cat(level, dim=0) for level in zip(*outs)]
+
+    def _decode(self, zs, start_level=0, end_level=None):
+        assert len(zs) == 1
+        with torch.cuda.device(self.device):
+            z = zs[0].to(device=self.device, dtype=torch.int64)
+            return self.decoder(self.bottleneck.decode(z))                          # [B, 8T', C]
+
+    def decode(self, zs, start_level=0, end_level=None, bs_chunks=1):
+        """[LongTensor [B, T']] -> Tensor [B, 8T', C]  (vqvae.py:152-159)."""
+        z_chunks = [torch.chunk(torch.as_tensor(z), bs_chunks, dim=0) for z in zs]
+        outs = [self._decode([zc[i] for zc in z_chunks], start_level, end_level) for i in range(bs_chunks)]
+        return torch.cat(outs, dim=0)
+
+    def sample(self, n_samples):
+        z = torch.randint(0, self.l_bins, size=(n_samples, self.hps.sample_length // self.hop), device=self.device)
+        return self.decode([z])
+
+    def forward(self, x):
+        raise NotImplementedError("training forward (losses, EMA codebook update) is outside the inference hot path")
+
+    __call__ = forward
