@@ -54,8 +54,8 @@ int qpg_version(void);
 const char* qpg_last_error(void);
 /* number of kernels this library has launched in the calling process */
 uint64_t qpg_launch_count(void);
-/* tuning hook for sweeps (0 = automatic): compute warps per CTA (8|12), ring depth, grid size */
-int qpg_tune_cosine(int compute_warps, int stages, int grid);
+/* tuning hook for sweeps (0 = automatic): compute warps per CTA (8|12), ring depth, grid size, team size */
+int qpg_tune_cosine(int compute_warps, int stages, int grid, int team);
 
 /* ---------------- packed window database ---------------------------------
  * Row-major float32 windows [W, D] are re-laid-out once per database into
@@ -86,6 +86,13 @@ int qpg_table_init(qpg_pair_t* table, int64_t n_entries, void* stream);
 int qpg_cand_cosine_minbycode(const float* packed, const double* row_sqnorm, const int32_t* labels,
                               int64_t W, int D, int64_t id_offset, const float* q, int Q,
                               qpg_pair_t* table, int queries_per_pass, void* stream);
+/* Same, with an explicit team size S in {1,2,3,4,6} (0 = automatic): the D range of a row
+ * group is split over S warps.  S fixes the float64 summation order of a dot product, so
+ * callers that merge tables from several GPUs pass the SAME S on every rank: identical rows
+ * then get bit-identical distances on every shard and exact ties keep the smallest id. */
+int qpg_cand_cosine_minbycode_team(const float* packed, const double* row_sqnorm, const int32_t* labels,
+                                   int64_t W, int D, int64_t id_offset, const float* q, int Q,
+                                   qpg_pair_t* table, int queries_per_pass, int team_size, void* stream);
 
 /* ---------------- candidate distance, Levenshtein, fused min-by-code -----
  * tokens [W, 12] uint32 (11 used: g0*320+g1 per tap, GestureKNN.py:58-60),

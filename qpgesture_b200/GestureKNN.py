@@ -179,9 +179,10 @@ class CodeKNN(object):
         if which == "text" or db.mode == "A":
             t = db.txt if which == "text" else db.aud
             assert q.dtype == torch.float32 and q.shape[1] == t.D, (q.shape, t.D)
-            _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
-                                                     t.W, t.D, db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), 0, sp),
-                       "qpg_cand_cosine_minbycode")
+            _lib.check(lib.qpg_cand_cosine_minbycode_team(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
+                                                          t.W, t.D, db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), 0,
+                                                          self._team_size(t.D), sp),
+                       "qpg_cand_cosine_minbycode_team")
         else:
             assert q.dtype == torch.int32 and q.shape[1] == 12
             _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W, db.id_offset,
@@ -189,6 +190,29 @@ class CodeKNN(object):
         if self.process_group is not None:
             table = self._merge_shards(table, stream)
         return table
+
+    def _team_size(self, D: int) -> int:
+        """Team size S for the cosine scan.  Single GPU: 0 (library picks).  Row-sharded: every rank must
+        use the same S (it fixes the float64 summation order, see qpg_cand_cosine_minbycode_team), so it is
+        derived from the largest shard of the WHOLE database, not from this rank's row count."""
+        if self.process_group is None:
+            return 0
+        import torch.distributed as dist
+
+        world = dist.get_world_size(self.process_group)
+        max_seq = -(-self.db.n_seq // world)
+        groups = -(-(max_seq * WINDOWS_PER_SEQ) // 8)
+        n_chunks = -(-D // 128)
+        sms = torch.cuda.get_device_properties(self.db.device).multi_processor_count
+        best, S = None, 1
+        for cand in (1, 2, 3, 4, 6):                      # same cost model as the library's automatic choice
+            if cand > n_chunks:
+                continue
+            teams = sms * (12 // cand)
+            cost = -(-groups // teams) * -(-n_chunks // cand)
+            if best is None or cost < best:
+                best, S = cost, cand
+        return S
 
     def _merge_shards(self, table, stream=None):
         import torch.distributed as dist

@@ -35,11 +35,12 @@ SIGNATURES = {
     "qpg_version": (_INT, []),
     "qpg_last_error": (C.c_char_p, []),
     "qpg_launch_count": (C.c_uint64, []),
-    "qpg_tune_cosine": (_INT, [_INT, _INT, _INT]),
+    "qpg_tune_cosine": (_INT, [_INT, _INT, _INT, _INT]),
     "qpg_packed_bytes": (C.c_size_t, [_I64, _INT]),
     "qpg_pack_rows_f32": (_INT, [_P, _I64, _INT, _P, _P, _P]),
     "qpg_table_init": (_INT, [_P, _I64, _P]),
     "qpg_cand_cosine_minbycode": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _P]),
+    "qpg_cand_cosine_minbycode_team": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _INT, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
     "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),

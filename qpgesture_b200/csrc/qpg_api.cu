@@ -31,7 +31,7 @@ int sm_count() {
   return cached[dev];
 }
 
-int cosine_set_tuning(int ncw, int ns, int grid);
+int cosine_set_tuning(int ncw, int ns, int grid, int team);
 
 }  // namespace qpg
 
@@ -42,6 +42,6 @@ extern "C" const char* qpg_last_error(void) { return qpg::g_err; }
 extern "C" uint64_t qpg_launch_count(void) { return qpg::g_launches.load(std::memory_order_relaxed); }
 
 // Tuning hook used by bench.py / profiles sweeps (not part of the reference surface).
-extern "C" int qpg_tune_cosine(int compute_warps, int stages, int grid) {
-  return qpg::cosine_set_tuning(compute_warps, stages, grid);
+extern "C" int qpg_tune_cosine(int compute_warps, int stages, int grid, int team) {
+  return qpg::cosine_set_tuning(compute_warps, stages, grid, team);
 }

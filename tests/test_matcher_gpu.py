@@ -19,7 +19,7 @@ def _torch():
     return torch
 
 
-def _scan_cosine(rows, labels, q, id_offset=0, qpp=0):
+def _scan_cosine(rows, labels, q, id_offset=0, qpp=0, team=0):
     """rows [W,D] f32, labels [W] -> numpy structured table [Q,512] via the C ABI."""
     torch = _torch()
     from qpgesture_b200 import _lib
@@ -33,8 +33,9 @@ def _scan_cosine(rows, labels, q, id_offset=0, qpp=0):
     tab = new_table(qd.shape[0], dev)
     sp = _lib.stream_ptr()
     _lib.check(lib.qpg_table_init(_lib.ptr(tab), tab.shape[0] * 512, sp), "init")
-    _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(pr.packed), _lib.ptr(pr.sqnorm), _lib.ptr(lab), pr.W, pr.D,
-                                             id_offset, _lib.ptr(qd), qd.shape[0], _lib.ptr(tab), qpp, sp), "cos")
+    _lib.check(lib.qpg_cand_cosine_minbycode_team(_lib.ptr(pr.packed), _lib.ptr(pr.sqnorm), _lib.ptr(lab), pr.W, pr.D,
+                                                  id_offset, _lib.ptr(qd), qd.shape[0], _lib.ptr(tab), qpp, team, sp),
+               "cos")
     torch.cuda.synchronize()
     return table_to_numpy(tab), pr
 
@@ -75,9 +76,29 @@ def test_cosine_queries_per_pass_and_offset():
     base, _ = _scan_cosine(rows, labels, q)
     for qpp in (1, 2, 4, 8):
         t, _ = _scan_cosine(rows, labels, q, qpp=qpp)
-        assert np.array_equal(t["id"], base["id"]) and np.array_equal(t["d"], base["d"])
+        # the pass width may change the warp-team split and with it the float64 summation order
+        assert np.array_equal(t["id"], base["id"]) and np.allclose(t["d"], base["d"], rtol=0, atol=1e-13)
     off, _ = _scan_cosine(rows, labels, q, id_offset=26 * 1000)
     assert np.array_equal(off["id"][base["id"] >= 0], base["id"][base["id"] >= 0] + 26000)
+
+
+@pytest.mark.parametrize("W,D,Q,team", [(300, 6144, 4, 2), (300, 6144, 3, 3), (1000, 1024, 5, 4), (90, 6144, 8, 6),
+                                        (2000, 384, 8, 3), (40, 512, 2, 4), (5000, 768, 4, 6), (3000, 256, 4, 2)])
+def test_cosine_team_split(W, D, Q, team):
+    """D range of a row group split over a team of warps: same windows, distances within 1e-12."""
+    rng = np.random.default_rng(W + D + team)
+    rows = rng.standard_normal((W, D)).astype(np.float32)
+    q = rng.standard_normal((Q, D)).astype(np.float32)
+    labels = rng.integers(0, 64, size=W)
+    rows[W // 2] = rows[1]
+    labels[W // 2] = labels[1]
+    table, _ = _scan_cosine(rows, labels, q, team=team)
+    for qi in range(Q):
+        (bd, bw), _ = _oracle_cosine_table(rows, labels, q[qi])
+        assert np.array_equal(table[qi]["id"], bw)
+        assert np.allclose(table[qi]["d"], bd, rtol=0, atol=1e-12)
+    again, _ = _scan_cosine(rows, labels, q, team=team)
+    assert np.array_equal(again["d"], table["d"])                 # deterministic bit for bit
 
 
 def test_sharded_scan_merges_to_full():

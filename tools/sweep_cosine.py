@@ -24,11 +24,13 @@ def main():
     try: peak = json.load(open("MEASURED_PEAKS.json"))["hbm_gbs"]
     except Exception: pass
     combos = [tuple(map(int, c.split(","))) for c in a.configs.split(";") if c] or \
-        [(qt, ncw, ns) for qt in (1, 2, 4, 8) for ncw in (8, 12) for ns in (2, 3, 4)]
+        [(qt, ncw, ns, 0) for qt in (1, 2, 4, 8) for ncw in (8, 12) for ns in (2, 3)]
     alg = a.W * (4 * a.D + 4)
-    for qt, ncw, ns in combos:
+    for combo in combos:
+        qt, ncw, ns = combo[:3]
+        team = combo[3] if len(combo) > 3 else 0
         tab = new_table(qt, dev)
-        lib.qpg_tune_cosine(ncw, ns, 0)
+        lib.qpg_tune_cosine(ncw, ns, 0, team)
         lib.qpg_table_init(_lib.ptr(tab), qt * 512, sp)
         def run():
             return lib.qpg_cand_cosine_minbycode(_lib.ptr(pr.packed), _lib.ptr(pr.sqnorm), _lib.ptr(labels), a.W, a.D, 0,
@@ -44,8 +46,8 @@ def main():
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / a.reps
         gbs = alg / ms / 1e6
-        print(f"W={a.W} D={a.D} qt={qt} ncw={ncw} ns={ns}: {ms*1e3:8.1f} us  {gbs:7.0f} GB/s  frac={gbs/peak:.3f}  per-query {ms*1e3/qt:7.1f} us")
-    lib.qpg_tune_cosine(0, 0, 0)
+        print(f"W={a.W} D={a.D} qt={qt} ncw={ncw} ns={ns} team={team}: {ms*1e3:8.1f} us  {gbs:7.0f} GB/s  frac={gbs/peak:.3f}  per-query {ms*1e3/qt:7.1f} us")
+    lib.qpg_tune_cosine(0, 0, 0, 0)
 
 if __name__ == "__main__":
     main()
