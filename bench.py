@@ -53,7 +53,8 @@ def parse():
     p.add_argument("--clips-per-gpu", type=int, default=1)
     p.add_argument("--cpu-sample-seq", type=int, default=32, help="database sequences in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--queries-per-pass", type=int, default=0)
+    p.add_argument("--row-shards", type=int, default=0, help="0 = plan_layout() decides")
+    p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     return p.parse_args()
 
 
@@ -212,53 +213,83 @@ def main():
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
-        pg = dist.group.WORLD
     lib = _lib.load()
+
+    # ---- layout: row shards x clip groups (qpgesture_b200/sharding.py: never cut a shard below the L2 size)
+    from qpgesture_b200.sharding import plan_layout, shard_sequences
+    db_bytes_total = args.n_seq * 26 * 4 * (6 * args.wavlm_dim + args.ctx_dim)
+    row_shards, clip_groups = plan_layout(db_bytes_total, world) if args.row_shards == 0 else \
+        (args.row_shards, world // args.row_shards)
+    assert row_shards * clip_groups == world
+    my_block, my_group = rank % row_shards, rank // row_shards
+    if row_shards > 1:
+        for gi in range(clip_groups):                      # every rank creates every group (NCCL requirement)
+            g_ = dist.new_group(list(range(gi * row_shards, (gi + 1) * row_shards)))
+            if gi == my_group:
+                pg = g_
+    else:
+        pg = None
 
     # ---- database (one-off, outside every timed region)
     arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
-    from qpgesture_b200.sharding import shard_sequences
-    j0, j1 = shard_sequences(args.n_seq, world, rank)
+    j0, j1 = shard_sequences(args.n_seq, row_shards, my_block)
     db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
                        aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
     knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg)
-    n_clips = args.clips_per_gpu * world
-    aq, tq, _, _ = make_clip_queries(n_clips, args.wavlm_dim, args.ctx_dim)
+    n_clips_total = args.clips_per_gpu * world
+    n_clips = args.clips_per_gpu * row_shards              # clips this rank's row group scans together
+    aq_all, tq_all, _, _ = make_clip_queries(n_clips_total, args.wavlm_dim, args.ctx_dim)
+    g_lo = my_group * n_clips
+    aq, tq = aq_all[g_lo:g_lo + n_clips], tq_all[g_lo:g_lo + n_clips]
     Q = n_clips * N_SEG * 8
     seed_rng = np.random.RandomState(123456)
     seeds = []
-    for _ in range(n_clips):
+    for _ in range(n_clips_total):
         i0 = seed_rng.randint(0, args.n_seq)
         j0_ = seed_rng.randint(0, 180 - 8)
         seeds.append((int(arrs["code"][i0, j0_ // 30]), arrs["phase_amp"][i0, j0_:j0_ + 8]))
+    seeds = seeds[g_lo:g_lo + n_clips]
     seed_code = np.array([s[0] for s in seeds], dtype=np.int32)
     seed_phase = np.stack([s[1] for s in seeds]).astype(np.float32)
-    my_clips = slice(rank * args.clips_per_gpu, (rank + 1) * args.clips_per_gpu)
+    my_clips = slice(my_block * args.clips_per_gpu, (my_block + 1) * args.clips_per_gpu)
 
     aq_h = torch.from_numpy(aq.reshape(Q, -1)).pin_memory()
     tq_h = torch.from_numpy(tq.reshape(Q, -1)).pin_memory()
-    aq_d, tq_d = aq_h.to(dev), tq_h.to(dev)
+    sc_h = torch.from_numpy(seed_code).pin_memory()
+    sp_h = torch.from_numpy(seed_phase).pin_memory()
     codes_h = torch.empty((args.clips_per_gpu, N_SEG, 30), dtype=torch.int64).pin_memory()
-    qpp = args.queries_per_pass
-
-    def scan_and_tail(qa, qt):
-        ta = knn._scan("audio", qa, new_table(Q, dev)) if qpp == 0 else _scan_qpp(knn, "audio", qa, Q, dev, qpp)
-        tt = knn._scan("text", qt, new_table(Q, dev)) if qpp == 0 else _scan_qpp(knn, "text", qt, Q, dev, qpp)
-        # tail of this rank's clips only
-        q0, q1 = my_clips.start * N_SEG * 8, my_clips.stop * N_SEG * 8
-        codes, vote, _, status = knn.tail_device(ta[q0:q1], tt[q0:q1], seed_code[my_clips], seed_phase[my_clips],
-                                                 args.clips_per_gpu, N_SEG, want_phase=False)
-        return codes, status
+    # the whole step (2 table inits, all scan passes, [all-gather + merge], 2 rank kernels, tail) is a fixed
+    # launch sequence over static buffers; by default it is captured once into a CUDA graph and replayed
+    use_graph = not args.no_graph
+    try:
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph)
+    except Exception as e:                                   # e.g. NCCL capture unsupported: plain launches
+        if rank == 0:
+            print(f"[bench] graph capture failed ({type(e).__name__}: {e}); using plain launches", file=sys.stderr)
+        use_graph = False
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False)
+    plan.qa.copy_(aq_h)
+    plan.qt.copy_(tq_h)
+    plan.seed_code.copy_(sc_h)
+    plan.seed_phase.copy_(sp_h)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    knn._launch_plan(plan)                                   # count our kernels in one step (graphs hide them)
+    torch.cuda.synchronize()
+    launches_per_step = _lib.launch_count() - l0
 
     def step_resident():
-        return scan_and_tail(aq_d, tq_d)
+        knn.run_plan(plan)
+        return plan.codes, plan.status
 
     def step_e2e():
-        qa = aq_h.to(dev, non_blocking=True)
-        qt = tq_h.to(dev, non_blocking=True)
-        codes, status = scan_and_tail(qa, qt)
-        codes_h.copy_(codes, non_blocking=True)
-        return codes, status
+        plan.qa.copy_(aq_h, non_blocking=True)
+        plan.qt.copy_(tq_h, non_blocking=True)
+        plan.seed_code.copy_(sc_h, non_blocking=True)
+        plan.seed_phase.copy_(sp_h, non_blocking=True)
+        knn.run_plan(plan)
+        codes_h.copy_(plan.codes, non_blocking=True)
+        return plan.codes, plan.status
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -278,7 +309,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
-        launches = _lib.launch_count() - l0
+        launches = launches_per_step * steps
         if world > 1:
             t = torch.tensor([ms], device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -294,7 +325,7 @@ def main():
 
     # ---- dominant kernel alone: one audio pass (one launch) at the library's queries-per-pass
     qpp_used = 4 if 6 * args.wavlm_dim > 2048 else 8
-    qa_small = aq_d[:qpp_used].contiguous()
+    qa_small = plan.qa[:qpp_used].contiguous()
     tab_small = new_table(qpp_used, dev)
     t = db.aud
     sp = _lib.stream_ptr()
@@ -326,20 +357,23 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = db.algorithmic_bytes("audio")
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
-        audio_seconds = n_clips * N_SEG * SEG_SECONDS
+        audio_seconds = n_clips_total * N_SEG * SEG_SECONDS
         line = dict(
             metric="seconds_of_audio_matched_per_second", value=audio_seconds / (ms_res * 1e-3), unit="s_audio/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
-                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu,
-                        query_steps_per_step=Q, db_bytes=int(db.aud.nbytes + db.txt.nbytes) * world,
-                        parallelism=f"rows sharded x{world}, all-gather + min-merge" if world > 1 else "single GPU",
+                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph),
+                        query_steps_per_rank_per_step=Q, db_bytes=int(db_bytes_total),
+                        parallelism=(f"{row_shards} row shards x {clip_groups} clip groups"
+                                     + (", all-gather + min-merge inside each row group" if row_shards > 1 else
+                                        ", database replicated, no data-path collective")) if world > 1
+                        else "single GPU",
                         l2="inputs larger than L2 (no flush needed)" if db.aud.nbytes > 126e6 else
                            "database shard fits L2; passes re-read it from L2"),
             e2e=dict(value=audio_seconds / (ms_e2e * 1e-3), unit="s_audio/s", ms_per_step=ms_e2e,
-                     h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4),
-                     d2h_bytes_per_step=int(codes_h.numel() * 8)),
+                     h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4 + sc_h.numel() * 4 + sp_h.numel() * 4) * world,
+                     d2h_bytes_per_step=int(codes_h.numel() * 8) * world),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", kernel=f"cand_cosine_kernel<QT={qpp_used}>", achieved=achieved, peak=peak,
                           unit="GB/s", frac=achieved / peak, traffic=None, launch_ms=pass_ms,
@@ -350,25 +384,15 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
         print(json.dumps(line))
+    sys.stdout.flush()
     if world > 1:
+        # Tear down without touching the NCCL communicator that the captured graph references:
+        # destroy_process_group() after a graph-captured collective can block for minutes.
+        del plan
+        torch.cuda.synchronize()
         dist.barrier()
-        dist.destroy_process_group()
-
-
-def _scan_qpp(knn, which, q, Q, dev, qpp):
-    from qpgesture_b200 import _lib
-    from qpgesture_b200.matchdb import new_table
-
-    lib, db = _lib.load(), knn.db
-    table = new_table(Q, dev)
-    sp = _lib.stream_ptr()
-    t = db.txt if which == "text" else db.aud
-    _lib.check(lib.qpg_table_init(_lib.ptr(table), Q * 512, sp), "init")
-    _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W, t.D,
-                                             db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), qpp, sp), "cosine")
-    if knn.process_group is not None:
-        table = knn._merge_shards(table)
-    return table
+        torch.cuda.synchronize()
+        os._exit(0)
 
 
 if __name__ == "__main__":

@@ -18,6 +18,7 @@ from __future__ import annotations
 import argparse
 import os
 import random
+from types import SimpleNamespace
 from typing import Optional
 
 import numpy as np
@@ -275,6 +276,93 @@ class CodeKNN(object):
             table = self._scan("text", q, new_table(1, dev))
         return self._lists_from_table(table_to_numpy(table)[0], "text")
 
+    # ---- preallocated plan: the whole step as a fixed launch sequence (optionally one CUDA graph) ------
+    def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False):
+        """Static device buffers for `n_clips` clips x `n_seg` segments.  `tail_clips` = slice of the
+        clips whose sequential tail this rank runs (default: all).  Fill plan.qa / plan.qt /
+        plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes."""
+        dev, db = self.db.device, self.db
+        Q = n_clips * n_seg * STEPS_PER_SEGMENT
+        tc = tail_clips if tail_clips is not None else slice(0, n_clips)
+        n_tail = tc.stop - tc.start
+        p = SimpleNamespace(n_clips=n_clips, n_seg=n_seg, Q=Q, tail=tc, n_tail=n_tail, graph=None)
+        with torch.cuda.device(dev):
+            if db.mode == "A":
+                p.qa = torch.zeros((Q, db.aud.D), dtype=torch.float32, device=dev)
+            else:
+                p.qa = torch.zeros((Q, 12), dtype=torch.int32, device=dev)
+            p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
+            p.seed_code = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
+            p.seed_phase = torch.zeros((n_clips, 8, 16), dtype=torch.float32, device=dev)
+            p.ta, p.tt = new_table(Q, dev), new_table(Q, dev)
+            if self.process_group is not None:
+                import torch.distributed as dist
+                world = dist.get_world_size(self.process_group)
+                p.parts_a = torch.empty((world, Q, codebook_size, 2), dtype=torch.int64, device=dev)
+                p.parts_t = torch.empty((world, Q, codebook_size, 2), dtype=torch.int64, device=dev)
+                p.ma, p.mt = new_table(Q, dev), new_table(Q, dev)
+            Qt = n_tail * n_seg * STEPS_PER_SEGMENT
+            p.ra = torch.empty((Qt, codebook_size), dtype=torch.int32, device=dev)
+            p.rt = torch.empty((Qt, codebook_size), dtype=torch.int32, device=dev)
+            p.codes = torch.empty((n_tail, n_seg, num_frames_code), dtype=torch.int64, device=dev)
+            p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
+            p.status = torch.zeros((n_tail,), dtype=torch.int32, device=dev)
+            p.phase = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
+                if want_phase else None
+            if use_graph:
+                self._launch_plan(p)                       # warm-up outside capture (sets function attributes)
+                torch.cuda.synchronize(dev)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._launch_plan(p)
+                p.graph = g
+        return p
+
+    def _launch_plan(self, p):
+        lib, db = _lib.load(), self.db
+        sp = _lib.stream_ptr()
+        for which, q, tab in (("audio", p.qa, p.ta), ("text", p.qt, p.tt)):
+            _lib.check(lib.qpg_table_init(_lib.ptr(tab), p.Q * codebook_size, sp), "qpg_table_init")
+            if which == "text" or db.mode == "A":
+                t = db.txt if which == "text" else db.aud
+                _lib.check(lib.qpg_cand_cosine_minbycode_team(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
+                                                              t.W, t.D, db.id_offset, _lib.ptr(q), p.Q, _lib.ptr(tab), 0,
+                                                              self._team_size(t.D), sp), "qpg_cand_cosine_minbycode_team")
+            else:
+                _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W, db.id_offset,
+                                                      _lib.ptr(q), p.Q, _lib.ptr(tab), sp), "qpg_cand_lev_minbycode")
+        ta, tt = p.ta, p.tt
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+            dist.all_gather_into_tensor(p.parts_a, p.ta, group=self.process_group)
+            dist.all_gather_into_tensor(p.parts_t, p.tt, group=self.process_group)
+            for parts, out in ((p.parts_a, p.ma), (p.parts_t, p.mt)):
+                _lib.check(lib.qpg_table_merge(_lib.ptr(parts), world, p.Q * codebook_size, _lib.ptr(out), sp),
+                           "qpg_table_merge")
+            ta, tt = p.ma, p.mt
+        per_clip = p.n_seg * STEPS_PER_SEGMENT
+        q0, q1 = p.tail.start * per_clip, p.tail.stop * per_clip
+        ta_s, tt_s = ta[q0:q1], tt[q0:q1]
+        Qt = q1 - q0
+        _lib.check(lib.qpg_rank512(_lib.ptr(ta_s), Qt, _lib.ptr(p.ra), sp), "qpg_rank512")
+        _lib.check(lib.qpg_rank512(_lib.ptr(tt_s), Qt, _lib.ptr(p.rt), sp), "qpg_rank512")
+        sc, sph = p.seed_code[p.tail], p.seed_phase[p.tail]
+        _lib.check(lib.qpg_match_tail(_lib.ptr(ta_s), _lib.ptr(tt_s), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank),
+                                      _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
+                                      _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(sc), _lib.ptr(sph),
+                                      p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote), _lib.ptr(p.phase),
+                                      _lib.ptr(p.status), sp), "qpg_match_tail")
+
+    def run_plan(self, p):
+        """Enqueue one step on the current stream (graph replay when the plan was captured)."""
+        with torch.cuda.device(self.db.device):
+            if p.graph is not None:
+                p.graph.replay()
+            else:
+                self._launch_plan(p)
+        return p.codes
+
     # ---- sequential tail ---------------------------------------------------------
     def tail_device(self, ta, tt, seed_code, seed_phase, n_clips, n_seg, want_phase=True):
         """ranks + match_tail kernels for n_clips x n_seg x 8 steps already scanned."""
@@ -384,13 +472,26 @@ class CodeKNN(object):
             seeds = [self.init_code_phase() for _ in range(n_clips)]
             seed_code = [s[0] for s in seeds]
             seed_phase = np.stack([s[1] for s in seeds])
-        ta, tt = self.match_tables(aud_q.reshape((Q,) + aud_q.shape[3:]), txt_q.reshape(Q, -1))
         if tail == "device":
-            codes, vote, _, status = self.tail_device(ta, tt, seed_code, seed_phase, n_clips, n_seg, want_phase=False)
-            codes_h = codes.cpu().numpy()
-            if int(status.max().cpu()) != 0:
-                raise IndexError("list index out of range")
+            key = (n_clips, n_seg)
+            plans = self.__dict__.setdefault("_plans", {})
+            if key not in plans:
+                plans[key] = self.make_plan(n_clips, n_seg, use_graph=self.process_group is None)
+            p = plans[key]
+            dev = self.db.device
+            with torch.cuda.device(dev):
+                p.qa.copy_(self._audio_query_tensor(aud_q.reshape((Q,) + aud_q.shape[3:])), non_blocking=True)
+                p.qt.copy_(torch.from_numpy(np.ascontiguousarray(txt_q.reshape(Q, -1), dtype=np.float32)),
+                           non_blocking=True)
+                p.seed_code.copy_(torch.from_numpy(np.asarray(seed_code, dtype=np.int32).reshape(n_clips)))
+                p.seed_phase.copy_(torch.from_numpy(np.ascontiguousarray(seed_phase, dtype=np.float32)
+                                                    .reshape(n_clips, 8, 16)))
+                self.run_plan(p)
+                codes_h = p.codes.cpu().numpy()
+                if int(p.status.max().cpu()) != 0:
+                    raise IndexError("list index out of range")
             return codes_h
+        ta, tt = self.match_tables(aud_q.reshape((Q,) + aud_q.shape[3:]), txt_q.reshape(Q, -1))
         ta_np = table_to_numpy(ta).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)
         tt_np = table_to_numpy(tt).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)
         out = np.empty((n_clips, n_seg, num_frames_code), dtype=np.int64)

@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(KB)
   __shared__ double s_dist[2];
   __shared__ long long s_win[2];
   __shared__ int s_frame[2];
+  __shared__ int s_code[2][4];
+  __shared__ float s_tail[2][8 * PC];
   __shared__ int s_fail;
 
   const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
@@ -88,101 +90,112 @@ __global__ void __launch_bounds__(KB)
   if (c == 0) s_fail = 0;
   int last = seed_code[b];
   const double freq_term = __dmul_rn((double)freq_rank[c], 0.05);
+  const int n_steps = n_seg * 8;
+  const size_t q0 = (size_t)b * n_steps;
+  // ranks and window ids of a step do not depend on the sequential state: keep one step in flight
+  int ra_n = aud_rank[q0 * KB + c], rt_n = txt_rank[q0 * KB + c];
+  long long ida_n = (long long)aud_table[q0 * KB + c].id, idt_n = (long long)txt_table[q0 * KB + c].id;
   __syncthreads();
 
-  for (int g = 0; g < n_seg; ++g) {
-    int code29 = last;
-    for (int s = 0; s < 8; ++s) {
-      const size_t q = ((size_t)b * n_seg + g) * 8 + s;
-      // pos_score + freq_score*0.05, then + rank (same IEEE operations as NumPy, GestureKNN.py:545,554,575)
-      const double base = __dadd_rn((double)pos_rank[(size_t)last * KB + c], freq_term);
-      ArgMin a{__dadd_rn(base, (double)aud_rank[q * KB + c]), c};
-      ArgMin t{__dadd_rn(base, (double)txt_rank[q * KB + c]), c};
-      a = warp_argmin(a);
-      t = warp_argmin(t);
-      if (lane == 0) {
-        red_a[warp] = a;
-        red_t[warp] = t;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        ArgMin x = lane < KB / 32 ? red_a[lane] : ArgMin{1e300, KB};
-        ArgMin y = lane < KB / 32 ? red_t[lane] : ArgMin{1e300, KB};
-        x = warp_argmin(x);
-        y = warp_argmin(y);
-        if (lane == 0) {
-          s_choice[0] = x.i;
-          s_choice[1] = y.i;
-        }
-      }
-      __syncthreads();
-      // warps 0 / 1 score the audio / text candidate by phase continuity (GestureKNN.py:627-644)
-      if (warp < 2) {
-        const Pair e = (warp == 0 ? aud_table : txt_table)[q * KB + s_choice[warp]];
-        const long long w = (long long)e.id;
-        if (w < 0 || w >= n_seq * WIN) {
-          if (lane == 0) s_fail = 1;
-        } else {
-          const long long j = w / WIN;
-          const int m = (int)(w - j * WIN);
-          const int f = (warp == 0 ? aud_frame : txt_frame)[m];
-          const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;  // rows f .. f+7
-          double av[4], bv[4], sa = 0.0, sb = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int e2 = lane + 32 * k, row = e2 >> 4, col = e2 & 15;
-            const float fa = row < 5 ? prev[(3 + row) * PC + col] : head[(row - 5) * PC + col];
-            const float fb = row < 3 ? prev[(5 + row) * PC + col] : head[(row - 3) * PC + col];
-            av[k] = (double)fa;
-            bv[k] = (double)fb;
-            sa = fma(av[k], av[k], sa);
-            sb = fma(bv[k], bv[k], sb);
-          }
-          sa = warp_sum(sa);
-          sb = warp_sum(sb);
-          const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
-          double acc = 0.0;
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const double d = av[k] / na - bv[k] / nb;
-            acc = fma(d, d, acc);
-          }
-          acc = 0.5 * warp_sum(acc);
-          if (lane == 0) {
-            s_dist[warp] = acc;
-            s_win[warp] = w;
-            s_frame[warp] = f;
-          }
-        }
-      }
-      __syncthreads();
-      if (s_fail) {
-        if (c == 0) status_out[b] = 1;
-        return;
-      }
-      const int final_idx = (s_dist[0] <= s_dist[1]) ? 0 : 1;  // tmp_distance.index(min(...)): audio wins ties
-      const long long w = s_win[final_idx];
-      const long long j = w / WIN;
-      const int m = (int)(w - j * WIN);
-      const int f = s_frame[final_idx];
-      float new_prev = 0.f;
-      if (c < 8 * PC) new_prev = phase_amp[((size_t)j * NFRM + f + 24) * PC + c];  // window frames 24..31
-      const int p1 = code[(size_t)j * NCODE + m + 1], p3 = code[(size_t)j * NCODE + m + 3];
-      if (c < 4) {
-        const int p = s * 4 + c;
-        if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = code[(size_t)j * NCODE + m + c];
-      }
-      if (c == 0) vote_out[q] = final_idx;
-      if (s == 7) code29 = p1;  // produced code #30 seeds the next segment (GestureKNN.py:800)
-      last = p3;
-      __syncthreads();  // everyone has read prev / s_* of this step
-      if (c < 8 * PC) {
-        prev[c] = new_prev;
-        if (phase_out) phase_out[(q * 8) * PC + c] = new_prev;
-      }
-      __syncthreads();
+  int code29 = last;
+  for (int st = 0; st < n_steps; ++st) {
+    const int g = st >> 3, s = st & 7;
+    const size_t q = q0 + st;
+    const int ra = ra_n, rt = rt_n;
+    const long long ida = ida_n, idt = idt_n;
+    // pos_score + freq_score*0.05, then + rank (same IEEE operations as NumPy, GestureKNN.py:545,554,575)
+    const int pr = pos_rank[(size_t)last * KB + c];
+    if (st + 1 < n_steps) {
+      ra_n = aud_rank[(q + 1) * KB + c];
+      rt_n = txt_rank[(q + 1) * KB + c];
+      ida_n = (long long)aud_table[(q + 1) * KB + c].id;
+      idt_n = (long long)txt_table[(q + 1) * KB + c].id;
     }
-    last = code29;
+    const double base = __dadd_rn((double)pr, freq_term);
+    ArgMin a{__dadd_rn(base, (double)ra), c};
+    ArgMin t{__dadd_rn(base, (double)rt), c};
+    a = warp_argmin(a);
+    t = warp_argmin(t);
+    if (lane == 0) {
+      red_a[warp] = a;
+      red_t[warp] = t;
+    }
+    __syncthreads();
+    {
+      // every warp reduces the 16 partials redundantly: no second hand-off through shared memory
+      ArgMin x = lane < KB / 32 ? red_a[lane] : ArgMin{1e300, KB};
+      ArgMin y = lane < KB / 32 ? red_t[lane] : ArgMin{1e300, KB};
+      x = warp_argmin(x);
+      y = warp_argmin(y);
+      if (c == x.i) s_win[0] = ida;
+      if (c == y.i) s_win[1] = idt;
+    }
+    __syncthreads();
+    // warps 0 / 1 score the audio / text candidate by phase continuity (GestureKNN.py:627-644)
+    if (warp < 2) {
+      const long long w = s_win[warp];
+      if (w < 0 || w >= n_seq * WIN) {
+        if (lane == 0) s_fail = 1;
+      } else {
+        const long long j = w / WIN;
+        const int m = (int)(w - j * WIN);
+        const int f = (warp == 0 ? aud_frame : txt_frame)[m];
+        const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;  // rows f .. f+7
+        if (lane < 4) s_code[warp][lane] = code[(size_t)j * NCODE + m + lane];
+        float tl[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) tl[k] = head[24 * PC + lane + 32 * k];   // window frames 24..31 (next prev)
+        double av[4], bv[4], sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int e2 = lane + 32 * k, row = e2 >> 4, col = e2 & 15;
+          const float fa = row < 5 ? prev[(3 + row) * PC + col] : head[(row - 5) * PC + col];
+          const float fb = row < 3 ? prev[(5 + row) * PC + col] : head[(row - 3) * PC + col];
+          av[k] = (double)fa;
+          bv[k] = (double)fb;
+          sa = fma(av[k], av[k], sa);
+          sb = fma(bv[k], bv[k], sb);
+        }
+        sa = warp_sum(sa);
+        sb = warp_sum(sb);
+        const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const double d = av[k] / na - bv[k] / nb;
+          acc = fma(d, d, acc);
+        }
+        acc = 0.5 * warp_sum(acc);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) s_tail[warp][lane + 32 * k] = tl[k];
+        if (lane == 0) {
+          s_dist[warp] = acc;
+          s_frame[warp] = f;
+        }
+      }
+    }
+    __syncthreads();
+    if (s_fail) {
+      if (c == 0) status_out[b] = 1;
+      return;
+    }
+    const int final_idx = (s_dist[0] <= s_dist[1]) ? 0 : 1;  // tmp_distance.index(min(...)): audio wins ties
+    float new_prev = 0.f;
+    if (c < 8 * PC) new_prev = s_tail[final_idx][c];
+    const int p1 = s_code[final_idx][1], p3 = s_code[final_idx][3];
+    if (c < 4) {
+      const int p = s * 4 + c;
+      if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = s_code[final_idx][c];
+    }
+    if (c == 0) vote_out[q] = final_idx;
+    if (s == 7) code29 = p1;  // produced code #30 seeds the next segment (GestureKNN.py:800)
+    last = (s == 7) ? code29 : p3;
+    __syncthreads();  // everyone has read prev / s_* of this step
+    if (c < 8 * PC) {
+      prev[c] = new_prev;
+      if (phase_out) phase_out[(q * 8) * PC + c] = new_prev;
+    }
+    __syncthreads();
   }
   if (c == 0) status_out[b] = 0;
 }
