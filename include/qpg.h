@@ -182,6 +182,31 @@ typedef struct {
 int qpg_conv1d_taps_f32(const qpg_conv_desc_t* desc, const float* in, const float* w, const float* bias,
                         const float* residual, float* out, void* stream);
 
+/* ---------------- tensor-core path of the same tap GEMM (tcgen05, kind::tf32) -------------
+ *   out[b, t, n] = bias[n] + residual[b, t, n]
+ *                + sum_tap sum_{k<C_in} in[b, t + row_offset[tap], chan_offset[tap] + k] * w[tap][n][k]
+ * `in` is a view [B, T_view, C_view] (float32, channels-last; C_view a multiple of 4): stride-2
+ * convolutions and the two phases of ConvTranspose1d(k4,s2,p1) are written on the paired-frame
+ * view [B, T/2, 2C] with channel offsets.  Rows outside [0, T_view) read as zero (conv padding).
+ * w is [n_taps][N_pad][K_pad] float32, zero padded (N_pad a multiple of BN, K_pad of 4).
+ * Output element (b, t, n) lives at out[(b*out_rows_per_item + t)*out_ld + out_chan_offset + n];
+ * `residual` uses the same addressing.  `out` and `out_relu` (= max(out, 0)) may each be NULL.
+ * Operands are rounded to TF32 by the tensor cores (about 1e-3 relative): fast mode, not the
+ * index-parity mode (that is qpg_conv1d_taps_f32, precision 0).
+ */
+typedef struct {
+  int B, T_view, C_view;
+  int n_out;
+  int C_in, C_out;
+  int K_pad, N_pad, BN;
+  int n_taps;
+  int row_offset[4];
+  int chan_offset[4];
+  int out_rows_per_item, out_ld, out_chan_offset;
+} qpg_conv_tc_desc_t;
+int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* desc, const float* in, const float* w, const float* bias,
+                         const float* residual, float* out, float* out_relu, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

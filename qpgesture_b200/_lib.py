@@ -26,6 +26,15 @@ class ConvDesc(C.Structure):
     ]
 
 
+class ConvTcDesc(C.Structure):
+    _fields_ = [
+        ("B", C.c_int), ("T_view", C.c_int), ("C_view", C.c_int), ("n_out", C.c_int), ("C_in", C.c_int),
+        ("C_out", C.c_int), ("K_pad", C.c_int), ("N_pad", C.c_int), ("BN", C.c_int), ("n_taps", C.c_int),
+        ("row_offset", C.c_int * 4), ("chan_offset", C.c_int * 4), ("out_rows_per_item", C.c_int),
+        ("out_ld", C.c_int), ("out_chan_offset", C.c_int),
+    ]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _INT = C.c_int
@@ -49,6 +58,7 @@ SIGNATURES = {
     "qpg_vq_argmin_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "qpg_vq_dequantise_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P]),
     "qpg_conv1d_taps_f32": (_INT, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "qpg_conv1d_taps_tf32": (_INT, [C.POINTER(ConvTcDesc), _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

@@ -165,6 +165,148 @@ class Decoder:
         return self.out(x, y, x.shape[1])
 
 
+# ======================================================================================
+# tensor-core ("fast", TF32) path: qpg_conv1d_taps_tf32
+# ======================================================================================
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+class _TcConv:
+    """One launch of qpg_conv1d_taps_tf32.  `w_taps` is a list of [C_out, C_in] matrices (one per
+    tap); they are stored [n_taps][N_pad][K_pad] zero padded, K-major, as the UMMA B operand."""
+
+    def __init__(self, w_taps, bias, row_offset, chan_offset, device):
+        c_out, c_in = w_taps[0].shape
+        self.c_in, self.c_out, self.n_taps = c_in, c_out, len(w_taps)
+        self.K_pad = _round_up(c_in, 4)
+        self.BN = min(256, _round_up(c_out, 16))
+        self.N_pad = _round_up(c_out, self.BN)
+        w = torch.zeros((self.n_taps, self.N_pad, self.K_pad), dtype=torch.float32, device=device)
+        for i, m in enumerate(w_taps):
+            w[i, :c_out, :c_in] = m.to(device=device, dtype=torch.float32)
+        self.w = w.contiguous()
+        self.bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
+        self.row_offset, self.chan_offset = list(row_offset), list(chan_offset)
+
+    def __call__(self, x, B, T_view, C_view, n_out, out=None, out_relu=None, residual=None, out_rows_per_item=None,
+                 out_ld=None, out_chan_offset=0):
+        lib = _lib.load()
+        d = _lib.ConvTcDesc()
+        d.B, d.T_view, d.C_view, d.n_out = B, T_view, C_view, n_out
+        d.C_in, d.C_out, d.K_pad, d.N_pad, d.BN, d.n_taps = self.c_in, self.c_out, self.K_pad, self.N_pad, self.BN, self.n_taps
+        for i in range(4):
+            d.row_offset[i] = self.row_offset[i] if i < self.n_taps else 0
+            d.chan_offset[i] = self.chan_offset[i] if i < self.n_taps else 0
+        d.out_rows_per_item = out_rows_per_item if out_rows_per_item is not None else n_out
+        d.out_ld = out_ld if out_ld is not None else self.c_out
+        d.out_chan_offset = out_chan_offset
+        _lib.check(lib.qpg_conv1d_taps_tf32(d, _lib.ptr(x), _lib.ptr(self.w), _lib.ptr(self.bias), _lib.ptr(residual),
+                                            _lib.ptr(out), _lib.ptr(out_relu), _lib.stream_ptr()),
+                   "qpg_conv1d_taps_tf32")
+
+
+class _TcResnet:
+    def __init__(self, sd, prefix, depth, growth, reverse, device):
+        dil = [growth ** d for d in range(depth)]
+        if reverse:
+            dil = dil[::-1]
+        self.blocks = []
+        for d in range(depth):
+            p = f"{prefix}.model.{d}.model"
+            w3, b3, w1, b1 = sd[p + ".1.weight"], sd[p + ".1.bias"], sd[p + ".3.weight"], sd[p + ".3.bias"]
+            conv3 = _TcConv([w3[:, :, k] for k in range(3)], b3, [-dil[d], 0, dil[d]], [0, 0, 0], device)
+            conv1 = _TcConv([w1[:, :, 0]], b1, [0], [0], device)
+            self.blocks.append((conv3, conv1))
+
+    def __call__(self, x_raw, x_relu):
+        """(raw, relu) -> raw of the last block (its ReLU copy is never needed by the next layer)."""
+        B, T, Cc = x_raw.shape
+        for i, (conv3, conv1) in enumerate(self.blocks):
+            h_relu = torch.empty_like(x_raw)
+            conv3(x_relu, B, T, Cc, T, out_relu=h_relu)
+            y_raw = torch.empty_like(x_raw)
+            last = i == len(self.blocks) - 1
+            y_relu = None if last else torch.empty_like(x_raw)
+            conv1(h_relu, B, T, Cc, T, out=y_raw, out_relu=y_relu, residual=x_raw)
+            x_raw, x_relu = y_raw, y_relu
+        return x_raw
+
+
+class TcEncoder:
+    """Encoder on tensor cores; the stride-2 k4 convolutions read the paired-frame view [B, T/2, 2C]."""
+
+    def __init__(self, sd, hps, device):
+        down_t, s = hps.downs_t[0], hps.strides_t[0]
+        assert s == 2
+        pre = "encoders.0.level_blocks.0.model"
+        self.downs, self.res, self.c_pad = [], [], []
+        for i in range(down_t):
+            w, b = sd[f"{pre}.{i}.0.weight"], sd[f"{pre}.{i}.0.bias"]            # [C_out, C_in, 4]
+            c_in = w.shape[1]
+            cp = _round_up(c_in, 4)                                              # channels of the (padded) input
+            self.c_pad.append(cp)
+            # t_in = 2t - 1 + k: k=0 -> pair t-1 second half, k=1 -> pair t first half, k=2 -> second half, k=3 -> pair t+1
+            self.downs.append(_TcConv([w[:, :, k] for k in range(4)], b, [-1, 0, 0, 1], [cp, 0, cp, 0], device))
+            self.res.append(_TcResnet(sd, f"{pre}.{i}.1", hps.depth, hps.dilation_growth_rate, False, device))
+        w, b = sd[f"{pre}.{down_t}.weight"], sd[f"{pre}.{down_t}.bias"]
+        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+
+    def __call__(self, x):
+        B, T, Cc = x.shape
+        if Cc != self.c_pad[0]:
+            x = torch.nn.functional.pad(x, (0, self.c_pad[0] - Cc)).contiguous()
+        for down, res, cp in zip(self.downs, self.res, self.c_pad):
+            B, T, Cc = x.shape
+            assert T % 2 == 0 and Cc == cp
+            raw = torch.empty((B, T // 2, down.c_out), dtype=torch.float32, device=x.device)
+            relu = torch.empty_like(raw)
+            down(x, B, T // 2, 2 * Cc, T // 2, out=raw, out_relu=relu)
+            x = res(raw, relu)
+        B, T, Cc = x.shape
+        y = torch.empty((B, T, self.out.c_out), dtype=torch.float32, device=x.device)
+        self.out(x, B, T, Cc, T, out=y)
+        return y
+
+
+class TcDecoder:
+    def __init__(self, sd, hps, device):
+        down_t, s = hps.downs_t[0], hps.strides_t[0]
+        assert s == 2
+        pre = "decoders.0.level_blocks.0.model"
+        w, b = sd[f"{pre}.0.weight"], sd[f"{pre}.0.bias"]
+        self.inp = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+        self.res, self.up_even, self.up_odd = [], [], []
+        for i in range(down_t):
+            self.res.append(_TcResnet(sd, f"{pre}.{i + 1}.0", hps.depth, hps.dilation_growth_rate,
+                                      hps.vqvae_reverse_decoder_dilation, device))
+            w, b = sd[f"{pre}.{i + 1}.1.weight"], sd[f"{pre}.{i + 1}.1.bias"]    # [C_in, C_out, 4]
+            wt = lambda k: w[:, :, k].t()
+            self.up_even.append(_TcConv([wt(1), wt(3)], b, [0, -1], [0, 0], device))
+            self.up_odd.append(_TcConv([wt(0), wt(2)], b, [1, 0], [0, 0], device))
+        w, b = sd["decoders.0.out.weight"], sd["decoders.0.out.bias"]
+        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+
+    def __call__(self, x):
+        B, T, Cc = x.shape
+        raw = torch.empty((B, T, self.inp.c_out), dtype=torch.float32, device=x.device)
+        relu = torch.empty_like(raw)
+        self.inp(x, B, T, Cc, T, out=raw, out_relu=relu)
+        n_up = len(self.res)
+        for i, (res, ue, uo) in enumerate(zip(self.res, self.up_even, self.up_odd)):
+            x = res(raw, relu)
+            B, T, Cc = x.shape
+            co = ue.c_out
+            raw = torch.empty((B, 2 * T, co), dtype=torch.float32, device=x.device)    # == paired view [B, T, 2*co]
+            relu = torch.empty_like(raw) if i < n_up - 1 else None
+            ue(x, B, T, Cc, T, out=raw, out_relu=relu, out_rows_per_item=T, out_ld=2 * co, out_chan_offset=0)
+            uo(x, B, T, Cc, T, out=raw, out_relu=relu, out_rows_per_item=T, out_ld=2 * co, out_chan_offset=co)
+        B, T, Cc = raw.shape
+        y = torch.empty((B, T, self.out.c_out), dtype=torch.float32, device=x.device)
+        self.out(raw, B, T, Cc, T, out=y)
+        return y
+
+
 class BottleneckBlock:
     """Inference half of bottleneck.py:15-154 (quantise / dequantise / encode / decode)."""
 
@@ -224,8 +366,12 @@ class VQVAE:
     # -- checkpoint ------------------------------------------------------------------
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         sd = _strip_module(state_dict)
-        self.encoder = Encoder(sd, self.hps, self.device, self.precision)
-        self.decoder = Decoder(sd, self.hps, self.device, self.precision)
+        if self.precision == 1:
+            self.encoder = TcEncoder(sd, self.hps, self.device)
+            self.decoder = TcDecoder(sd, self.hps, self.device)
+        else:
+            self.encoder = Encoder(sd, self.hps, self.device, self.precision)
+            self.decoder = Decoder(sd, self.hps, self.device, self.precision)
         self.bottleneck.k = sd["bottleneck.level_blocks.0.k"].to(device=self.device, dtype=torch.float32).contiguous()
         return self
 

@@ -132,3 +132,81 @@ def test_visualize_code_and_cal_distance(tmp_path):
     want_all = vr.decode(torch.from_numpy(c), sd, hps).numpy()
     assert p.shape == (64, 240, 135) and np.allclose(p, want_all, rtol=0, atol=2e-4)
     assert np.allclose(sig, want_all.mean(1), rtol=0, atol=2e-4)
+
+
+# ---------------------------------------------------------------------------------------------
+# tensor-core (tcgen05, TF32 operands) fast path.  Stated tolerance: TF32 rounds both operands to
+# 10 mantissa bits (2^-11 relative per element); a layer output therefore agrees with float32 to
+# ~1e-3 of its magnitude, the 19-layer stacks to ~1e-2 of the output scale.  Code indices are
+# compared as an agreement RATE (the fp32 FFMA path above is the index-parity mode).
+# ---------------------------------------------------------------------------------------------
+def _rel_err(got, want):
+    return float((got - want).abs().max() / want.abs().max().clamp_min(1e-6))
+
+
+def test_tc_single_layers_vs_torch():
+    import torch.nn.functional as F
+
+    from qpgesture_b200.vqvae import _TcConv
+
+    g = torch.Generator().manual_seed(1)
+    dev = "cuda"
+    # (a) dilated k3 conv, 512 -> 512, residual, raw + relu outputs; T = 30 (4 items per tile) and batch tail
+    B, T, Cc = 7, 30, 512
+    x = torch.randn((B, T, Cc), generator=g)
+    w = torch.randn((Cc, Cc, 3), generator=g) * 0.03
+    b = torch.randn((Cc,), generator=g)
+    want = x + F.conv1d(x.permute(0, 2, 1), w, b, padding=9, dilation=9).permute(0, 2, 1)
+    conv = _TcConv([w[:, :, k] for k in range(3)], b, [-9, 0, 9], [0, 0, 0], dev)
+    xd = x.to(dev)
+    raw, relu = torch.empty_like(xd), torch.empty_like(xd)
+    conv(xd, B, T, Cc, T, out=raw, out_relu=relu, residual=xd)
+    assert _rel_err(raw.cpu(), want) < 3e-3, _rel_err(raw.cpu(), want)
+    assert torch.equal(relu, raw.clamp_min(0))
+    # (b) stride-2 k4 conv on the paired view, C_in = 135 padded to 136, T = 240 (two 128-row tiles, second partial)
+    B, T, Ci, Co = 2, 240, 135, 512
+    x = torch.randn((B, T, Ci), generator=g)
+    w = torch.randn((Co, Ci, 4), generator=g) * 0.05
+    b = torch.randn((Co,), generator=g)
+    want = F.conv1d(x.permute(0, 2, 1), w, b, stride=2, padding=1).permute(0, 2, 1)
+    xp = F.pad(x, (0, 1)).contiguous().to(dev)
+    conv = _TcConv([w[:, :, k] for k in range(4)], b, [-1, 0, 0, 1], [136, 0, 136, 0], dev)
+    out = torch.empty((B, T // 2, Co), device=dev)
+    conv(xp, B, T // 2, 272, T // 2, out=out)
+    assert _rel_err(out.cpu(), want) < 3e-3, _rel_err(out.cpu(), want)
+    # (c) transposed k4 s2 p1 as two phases into the paired output view; (d) 512 -> 135 with scalar stores
+    B, T, Ci, Co = 3, 60, 512, 512
+    x = torch.randn((B, T, Ci), generator=g)
+    w = torch.randn((Ci, Co, 4), generator=g) * 0.03
+    b = torch.randn((Co,), generator=g)
+    want = F.conv_transpose1d(x.permute(0, 2, 1), w, b, stride=2, padding=1).permute(0, 2, 1)
+    xd = x.to(dev)
+    out = torch.empty((B, 2 * T, Co), device=dev)
+    wt = lambda k: w[:, :, k].t()
+    _TcConv([wt(1), wt(3)], b, [0, -1], [0, 0], dev)(xd, B, T, Ci, T, out=out, out_rows_per_item=T, out_ld=2 * Co)
+    _TcConv([wt(0), wt(2)], b, [1, 0], [0, 0], dev)(xd, B, T, Ci, T, out=out, out_rows_per_item=T, out_ld=2 * Co,
+                                                   out_chan_offset=Co)
+    assert _rel_err(out.cpu(), want) < 3e-3, _rel_err(out.cpu(), want)
+    w = torch.randn((135, Ci, 3), generator=g) * 0.03
+    b = torch.randn((135,), generator=g)
+    want = F.conv1d(x.permute(0, 2, 1), w, b, padding=1).permute(0, 2, 1)
+    out = torch.empty((B, T, 135), device=dev)
+    _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], dev)(xd, B, T, Ci, T, out=out)
+    assert _rel_err(out.cpu(), want) < 3e-3, _rel_err(out.cpu(), want)
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_tc_encode_decode_vs_golden(path):
+    from qpgesture_b200.vqvae import VQVAE
+
+    fx, hps, sd, x = load_vq_case(path)
+    model = VQVAE(hps, 135, device="cuda", precision=1).load_state_dict(sd)
+    lat = model.latents(x).cpu().numpy().reshape(-1, hps.emb_width)
+    scale = np.abs(fx["latents"]).max()
+    assert np.abs(lat - fx["latents"]).max() < 2e-2 * scale, np.abs(lat - fx["latents"]).max() / scale
+    codes = model.encode(x)[0].cpu().numpy()
+    agree = (codes == fx["codes"]).mean()
+    assert agree >= 0.7, agree                      # fast mode: agreement rate, not identity
+    dec = model.decode([torch.from_numpy(fx["codes"])]).cpu().numpy()
+    dscale = np.abs(fx["decoded"]).max()
+    assert np.abs(dec - fx["decoded"]).max() < 2e-2 * dscale, np.abs(dec - fx["decoded"]).max() / dscale
