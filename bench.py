@@ -356,6 +356,13 @@ def main():
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
         alg_bytes = db.algorithmic_bytes("audio")
+        traffic = None                                       # dram read+write per launch from the ncu --set full capture
+        try:
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_cosine_traffic.json")))
+            if tr["W"] == db.W and tr["D"] == db.aud.D:
+                traffic = tr["dram_bytes_per_launch"]
+        except Exception:
+            pass
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
         audio_seconds = n_clips_total * N_SEG * SEG_SECONDS
         line = dict(
@@ -376,7 +383,7 @@ def main():
                      d2h_bytes_per_step=int(codes_h.numel() * 8) * world),
             gpu_launches=int(launches),
             roofline=dict(bound="hbm", kernel=f"cand_cosine_kernel<QT={qpp_used}>", achieved=achieved, peak=peak,
-                          unit="GB/s", frac=achieved / peak, traffic=None, launch_ms=pass_ms,
+                          unit="GB/s", frac=achieved / peak, traffic=traffic, launch_ms=pass_ms,
                           algorithmic_bytes=int(alg_bytes),
                           peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"),
             clocks=clocks,

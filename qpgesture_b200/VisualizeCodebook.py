@@ -107,5 +107,21 @@ def main(argv=None):
     return visualize_code(config, a.VQVAE_model_path, a.save_path, a.prefix, code_source, model=model)
 
 
+
+def dataset_to_code(poses, model, data_mean=None, data_std=None, batch=256):
+    """Bulk version of process/make_beat_dataset.py:291-325 (`subdataset_to_code`): normalise
+    (x - mean) / clip(std, 0.01) and encode.  The reference encodes one [1,240,135] sequence per call;
+    here sequences go through the encoder `batch` at a time.  poses [N, 240, 135] -> int64 codes [N, 30]."""
+    x = np.asarray(poses, dtype=np.float64)
+    if data_mean is not None:
+        std = np.clip(np.asarray(data_std, dtype=np.float64).squeeze(), a_min=0.01, a_max=None)
+        x = (x - np.asarray(data_mean, dtype=np.float64).squeeze()) / std
+    out = []
+    for i in range(0, x.shape[0], batch):
+        zs = model.encode(torch.from_numpy(x[i:i + batch]).float())
+        out.append(zs[0].cpu().numpy())
+    return np.concatenate(out, axis=0) if out else np.zeros((0, 0), dtype=np.int64)
+
+
 if __name__ == "__main__":
     main()

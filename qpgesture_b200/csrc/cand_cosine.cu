@@ -465,8 +465,9 @@ static int cosine_scan(const float* packed, const double* row_sqnorm, const int3
   int ns = g_tuning.ns ? g_tuning.ns : 3;
   int pool = ns * ncw;
   if (pool > tiles_fit) pool = tiles_fit;
-  const int64_t max_useful = (G * S + ncw - 1) / ncw;
-  if (grid > max_useful) grid = (int)max_useful;
+  // keep every SM busy: row groups are spread evenly over all CTAs (some warps idle) rather than
+  // packed into fewer, fuller CTAs; only shrink the grid when there are fewer groups than CTAs
+  if (grid > G) grid = (int)G;
   if (grid < 1) grid = 1;
 
   Pair* tab = reinterpret_cast<Pair*>(table);

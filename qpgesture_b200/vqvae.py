@@ -349,8 +349,10 @@ class BottleneckBlock:
 class VQVAE:
     """Inference surface of models/vqvae.py:52-181 (levels = 1)."""
 
-    def __init__(self, hps, input_dim=72, device=None, precision=0):
+    def __init__(self, hps, input_dim=72, device=None, precision=0, use_graph=True, max_graphs=8):
+        """precision 0 = float32 FFMA (index-parity mode), 1 = tcgen05 TF32 tensor cores (fast mode)."""
         assert hps.levels == 1, "the reference config uses one level (codebook.yml:3)"
+        self.use_graph, self.max_graphs, self._graphs = use_graph, max_graphs, {}
         _lib.load()
         self.hps = hps
         self.input_dim = input_dim
@@ -366,6 +368,7 @@ class VQVAE:
     # -- checkpoint ------------------------------------------------------------------
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         sd = _strip_module(state_dict)
+        self._graphs = {}
         if self.precision == 1:
             self.encoder = TcEncoder(sd, self.hps, self.device)
             self.decoder = TcDecoder(sd, self.hps, self.device)
@@ -391,10 +394,33 @@ class VQVAE:
         with torch.cuda.device(self.device):
             return self.encoder(self.preprocess(x))
 
+    # -- per-shape CUDA graphs: an encode / decode is ~25 dependent launches of microsecond kernels, so the
+    #    fixed launch sequence for a given input shape is captured once and replayed (static in/out buffers)
+    def _graphed(self, kind, x, fn):
+        if not self.use_graph:
+            return fn(x)
+        key = (kind, tuple(x.shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+            static_in = x.clone()
+            fn(static_in)                                   # warm-up: function attributes, allocator
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                static_out = fn(static_in)
+            ent = (g, static_in, static_out)
+            self._graphs[key] = ent
+        g, static_in, static_out = ent
+        static_in.copy_(x)
+        g.replay()
+        return static_out.clone()
+
     def _encode(self, x, start_level=0, end_level=None):
         with torch.cuda.device(self.device):
-            h = self.encoder(self.preprocess(x))
-            return [self.bottleneck.encode(h)][start_level:end_level]
+            codes = self._graphed("enc", self.preprocess(x), lambda t: self.bottleneck.encode(self.encoder(t)))
+            return [codes][start_level:end_level]
 
     def encode(self, x, start_level=0, end_level=None, bs_chunks=1):
         """x [B, T, C] -> [LongTensor [B, T/8]]  (vqvae.py:174-181)."""
@@ -405,8 +431,8 @@ class VQVAE:
     def _decode(self, zs, start_level=0, end_level=None):
         assert len(zs) == 1
         with torch.cuda.device(self.device):
-            z = zs[0].to(device=self.device, dtype=torch.int64)
-            return self.decoder(self.bottleneck.decode(z))                          # [B, 8T', C]
+            z = zs[0].to(device=self.device, dtype=torch.int64).contiguous()
+            return self._graphed("dec", z, lambda t: self.decoder(self.bottleneck.decode(t)))   # [B, 8T', C]
 
     def decode(self, zs, start_level=0, end_level=None, bs_chunks=1):
         """[LongTensor [B, T']] -> Tensor [B, 8T', C]  (vqvae.py:152-159)."""

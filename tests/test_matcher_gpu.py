@@ -305,3 +305,86 @@ def test_cli_end_to_end_files():
     want = om.predict_codes(db, aq, tq, ties="numpy", freq_score=freq_rank_from_code(code), report=rep)
     assert got.shape == (3, 30) and got.dtype == np.int64
     assert np.array_equal(got, want)
+
+
+def test_empty_and_degenerate_inputs():
+    """W = 0, Q = 0 and single-row tables are accepted and leave the sentinel table untouched / correct."""
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import new_table, table_to_numpy
+
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    tab = new_table(3, dev)
+    sp = _lib.stream_ptr()
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab), 3 * 512, sp), "init")
+    dummy = torch.zeros(1024, dtype=torch.float32, device=dev)
+    dd = torch.zeros(8, dtype=torch.float64, device=dev)
+    lab = torch.zeros(8, dtype=torch.int32, device=dev)
+    assert lib.qpg_cand_cosine_minbycode(_lib.ptr(dummy), _lib.ptr(dd), _lib.ptr(lab), 0, 128, 0, _lib.ptr(dummy), 3,
+                                         _lib.ptr(tab), 0, sp) == 0
+    assert lib.qpg_cand_cosine_minbycode(_lib.ptr(dummy), _lib.ptr(dd), _lib.ptr(lab), 8, 128, 0, _lib.ptr(dummy), 0,
+                                         _lib.ptr(tab), 0, sp) == 0
+    t = table_to_numpy(tab)
+    assert np.all(t["d"] == 1e3) and np.all(t["id"] == -1)
+    # bad arguments are reported, not executed
+    assert lib.qpg_cand_cosine_minbycode(None, _lib.ptr(dd), _lib.ptr(lab), 8, 128, 0, _lib.ptr(dummy), 1,
+                                         _lib.ptr(tab), 0, sp) < 0
+    assert b"null" in lib.qpg_last_error()
+    assert lib.qpg_cand_cosine_minbycode(_lib.ptr(dummy), _lib.ptr(dd), _lib.ptr(lab), 8, 128, 0, _lib.ptr(dummy), 1,
+                                         _lib.ptr(tab), 9, sp) < 0
+    # one row, one query, label out of range is ignored like an absent code
+    rows = np.ones((1, 128), dtype=np.float32)
+    tb, _ = _scan_cosine(rows, np.array([600]), rows)
+    assert np.all(tb["id"] == -1)
+    tb, _ = _scan_cosine(rows, np.array([7]), rows)
+    assert tb["id"][0, 7] == 0 and tb["d"][0, 7] < 1e-12       # 1 - <x,x>/(|x||x|) up to one rounding
+
+
+def test_full_size_speaker10_properties():
+    """BASELINE size (13 312 windows x 6144-d): oracle check on two queries plus size-independent
+    properties: idempotence (re-scan into the same table changes nothing), shard-and-merge == full scan,
+    and a query that is a database window finds itself at distance 0."""
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import PackedRows, new_table, table_to_numpy
+
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    W, D, Q = 13312, 6144, 6
+    g = torch.Generator(device=dev)
+    g.manual_seed(0)
+    rows_d = torch.randn((W, D), device=dev, generator=g)
+    labels = torch.randint(0, 512, (W,), device=dev, dtype=torch.int32, generator=g)
+    q = torch.randn((Q, D), device=dev, generator=g)
+    q[0] = rows_d[4321]
+    pr = PackedRows.from_rows(rows_d)
+    sp = _lib.stream_ptr()
+
+    def scan(packed, sqn, lab, w, off, tab):
+        _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(packed), _lib.ptr(sqn), _lib.ptr(lab), w, D, off, _lib.ptr(q),
+                                                 Q, _lib.ptr(tab), 0, sp), "cos")
+    tab = new_table(Q, dev)
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab), Q * 512, sp), "init")
+    scan(pr.packed, pr.sqnorm, labels, W, 0, tab)
+    full = table_to_numpy(tab).copy()
+    scan(pr.packed, pr.sqnorm, labels, W, 0, tab)                      # idempotent
+    again = table_to_numpy(tab)
+    assert np.array_equal(again["id"], full["id"]) and np.array_equal(again["d"], full["d"])
+    lab_h = labels.cpu().numpy()
+    assert full["id"][0, lab_h[4321]] == 4321 and full["d"][0, lab_h[4321]] < 1e-12
+    # two shards scanned into ONE table (refinement) == full scan
+    half = 26 * 256
+    tab2 = new_table(Q, dev)
+    _lib.check(lib.qpg_table_init(_lib.ptr(tab2), Q * 512, sp), "init")
+    for a, b in ((0, half), (half, W)):
+        prs = PackedRows.from_rows(rows_d[a:b].contiguous())
+        scan(prs.packed, prs.sqnorm, labels[a:b].contiguous(), b - a, a, tab2)
+    both = table_to_numpy(tab2)
+    assert np.array_equal(both["id"], full["id"]) and np.allclose(both["d"], full["d"], rtol=0, atol=1e-13)
+    # oracle on two queries (float64 sklearn arithmetic over the whole table)
+    rows_h = rows_d.cpu().numpy()
+    for qi in (1, 5):
+        (bd, bw), _ = _oracle_cosine_table(rows_h, lab_h, q[qi].cpu().numpy())
+        assert np.array_equal(full[qi]["id"], bw)
+        assert np.allclose(full[qi]["d"], bd, rtol=0, atol=1e-12)

@@ -210,3 +210,20 @@ def test_tc_encode_decode_vs_golden(path):
     dec = model.decode([torch.from_numpy(fx["codes"])]).cpu().numpy()
     dscale = np.abs(fx["decoded"]).max()
     assert np.abs(dec - fx["decoded"]).max() < 2e-2 * dscale, np.abs(dec - fx["decoded"]).max() / dscale
+
+
+def test_dataset_to_code_bulk_matches_per_sequence():
+    """Row 8(f).2: batched dataset_to_code == the reference's one-sequence-at-a-time loop (oracle encode)."""
+    from qpgesture_b200 import VisualizeCodebook as VC
+
+    hps = vr.make_hps(width=32, emb_width=32, l_bins=64)
+    sd = vr.random_state_dict(hps, 135, seed=4, codebook_seed=5)
+    model = _model(hps, sd)
+    rng = np.random.default_rng(2)
+    poses = rng.standard_normal((9, 240, 135)) * 0.1 + 0.5
+    mean, std = rng.standard_normal(135) * 0.1 + 0.5, rng.random(135) * 0.2
+    got = VC.dataset_to_code(poses, model, mean, std, batch=4)
+    stdc = np.clip(std, 0.01, None)
+    want = np.stack([vr.encode(torch.from_numpy(((p - mean) / stdc)[None]).float(), sd, hps)[0].numpy() for p in poses])
+    assert got.shape == (9, 30)
+    assert (got == want).mean() >= 0.99
