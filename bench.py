@@ -54,7 +54,9 @@ def parse():
     p.add_argument("--cpu-sample-seq", type=int, default=32, help="database sequences in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--row-shards", type=int, default=0, help="0 = plan_layout() decides")
+    p.add_argument("--no-vqvae", action="store_true", help="skip the informational VQ-VAE block")
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    p.add_argument("--no-overlap", action="store_true", help="do not overlap the sequential tail with the scans")
     return p.parse_args()
 
 
@@ -189,6 +191,45 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+# ------------------------------------------------------------------ VQ-VAE (BASELINE.json configs[1], informational)
+def vqvae_block(dev, B=4096, T=8):
+    """encode -> quantise -> decode of synthetic 8-frame pose batches on the tcgen05 TF32 path (random-init
+    weights of the codebook.yml architecture), index agreement against the float32 FFMA parity path."""
+    import torch
+    from qpgesture_b200.synth import random_vqvae_state_dict, vqvae_hps
+    from qpgesture_b200.vqvae import VQVAE
+
+    hps = vqvae_hps()
+    sd = random_vqvae_state_dict(hps, 135, seed=0, codebook_seed=1)
+    x = torch.randn((B, T, 135), generator=torch.Generator().manual_seed(0)).to(dev)
+    out = {}
+    codes = {}
+    for prec, name in ((1, "tf32_tcgen05"), (0, "fp32_ffma")):
+        m = VQVAE(hps, 135, device=dev, precision=prec).load_state_dict(sd)
+        reps = 10 if prec == 1 else 2
+        for _ in range(2):
+            zs = m.encode(x)
+            m.decode(zs)
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        for _ in range(reps):
+            zs = m.encode(x)
+        e1.record()
+        for _ in range(reps):
+            y = m.decode(zs)
+        e2.record()
+        torch.cuda.synchronize()
+        enc_ms, dec_ms = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
+        codes[name] = zs[0]
+        out[name] = dict(encode_ms=enc_ms, decode_ms=dec_ms, codes_per_s=B * T / 8 / enc_ms * 1e3,
+                         decoded_frames_per_s=B * T / dec_ms * 1e3,
+                         encode_tflops=1.6235 * B * T / 240 / enc_ms, decode_tflops=1.9083 * B * T / 240 / dec_ms)
+    out["index_agreement_tf32_vs_fp32"] = float((codes["tf32_tcgen05"] == codes["fp32_ffma"]).float().mean())
+    out["shape"] = [B, T, 135]
+    return out
+
+
 # ------------------------------------------------------------------ our arm
 def main():
     args = parse()
@@ -262,12 +303,13 @@ def main():
     # launch sequence over static buffers; by default it is captured once into a CUDA graph and replayed
     use_graph = not args.no_graph
     try:
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph)
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph,
+                             overlap_tail=not args.no_overlap)
     except Exception as e:                                   # e.g. NCCL capture unsupported: plain launches
         if rank == 0:
             print(f"[bench] graph capture failed ({type(e).__name__}: {e}); using plain launches", file=sys.stderr)
         use_graph = False
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False)
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=not args.no_overlap)
     plan.qa.copy_(aq_h)
     plan.qt.copy_(tq_h)
     plan.seed_code.copy_(sc_h)
@@ -370,7 +412,7 @@ def main():
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
             scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
-                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph),
+                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph), tail_overlapped=bool(plan.overlap),
                         query_steps_per_rank_per_step=Q, db_bytes=int(db_bytes_total),
                         parallelism=(f"{row_shards} row shards x {clip_groups} clip groups"
                                      + (", all-gather + min-merge inside each row group" if row_shards > 1 else
@@ -388,6 +430,8 @@ def main():
                           peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"),
             clocks=clocks,
         )
+        if world == 1 and not args.no_vqvae:
+            line["vqvae"] = vqvae_block(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
         print(json.dumps(line))

@@ -146,6 +146,19 @@ int qpg_match_tail(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, con
                    int n_clips, int n_seg, int64_t* codes_out, int32_t* vote_out, float* phase_out,
                    int32_t* status_out, void* stream);
 
+/* Same state machine, one launch per run of segments [seg_begin, seg_begin+seg_count): `state`
+ * (float32 [n_clips, 132], caller owned) carries (last code, failure flag, previous phase) from one
+ * launch to the next, so the tail of segment g can run on a side stream as soon as that segment's
+ * tables exist while later segments are still being scanned.  Tables / ranks / outputs are indexed by
+ * the ABSOLUTE step (clip*n_seg*8 + seg*8 + s); seeds are read only when seg_begin == 0. */
+int qpg_match_tail_segments(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, const int32_t* aud_rank,
+                            const int32_t* txt_rank, const int32_t* pos_rank, const int32_t* freq_rank,
+                            const int32_t* code, int64_t n_seq, const float* phase_amp, const int32_t* aud_frame,
+                            const int32_t* txt_frame, const int32_t* seed_code, const float* seed_phase,
+                            int n_clips, int n_seg, int seg_begin, int seg_count, float* state,
+                            int64_t* codes_out, int32_t* vote_out, float* phase_out, int32_t* status_out,
+                            void* stream);
+
 /* ---------------- VQ codebook L2 argmin -----------------------------------
  * BottleneckBlock.quantise (codebook/models/bottleneck.py:120-126):
  *   dist[m][k] = fl32( fl32(|x_m|^2 - 2*<x_m,c_k>) + |c_k|^2 ),  idx = first argmin

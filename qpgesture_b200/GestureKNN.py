@@ -277,7 +277,8 @@ class CodeKNN(object):
         return self._lists_from_table(table_to_numpy(table)[0], "text")
 
     # ---- preallocated plan: the whole step as a fixed launch sequence (optionally one CUDA graph) ------
-    def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False):
+    def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False,
+                  overlap_tail: bool = True):
         """Static device buffers for `n_clips` clips x `n_seg` segments.  `tail_clips` = slice of the
         clips whose sequential tail this rank runs (default: all).  Fill plan.qa / plan.qt /
         plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes."""
@@ -286,7 +287,11 @@ class CodeKNN(object):
         tc = tail_clips if tail_clips is not None else slice(0, n_clips)
         n_tail = tc.stop - tc.start
         p = SimpleNamespace(n_clips=n_clips, n_seg=n_seg, Q=Q, tail=tc, n_tail=n_tail, graph=None)
+        # one clip on one GPU: overlap each segment's rank + tail with the scans of the following segments
+        p.overlap = bool(overlap_tail) and n_clips == 1 and n_tail == 1 and self.process_group is None
         with torch.cuda.device(dev):
+            p.side_stream = torch.cuda.Stream(device=dev) if p.overlap else None
+            p.state = torch.zeros((max(n_tail, 1), 8 * 16 + 4), dtype=torch.float32, device=dev)
             if db.mode == "A":
                 p.qa = torch.zeros((Q, db.aud.D), dtype=torch.float32, device=dev)
             else:
@@ -318,7 +323,51 @@ class CodeKNN(object):
                 p.graph = g
         return p
 
+    def _launch_plan_overlapped(self, p):
+        """Single clip, single GPU: segment g's ranks + tail run on a side stream (one SM is left free for
+        them) while the main stream already scans segment g+1.  Same kernels, same results."""
+        lib, db = _lib.load(), self.db
+        main = torch.cuda.current_stream()
+        side = p.side_stream
+        sms = torch.cuda.get_device_properties(db.device).multi_processor_count
+        S8 = STEPS_PER_SEGMENT
+        sp = _lib.stream_ptr(main)
+        _lib.check(lib.qpg_table_init(_lib.ptr(p.ta), p.Q * codebook_size, sp), "qpg_table_init")
+        _lib.check(lib.qpg_table_init(_lib.ptr(p.tt), p.Q * codebook_size, sp), "qpg_table_init")
+        lib.qpg_tune_cosine(0, 0, sms - 1, 0)
+        try:
+            for g in range(p.n_seg):
+                qs = slice(g * S8, (g + 1) * S8)
+                for which, q, tab in (("audio", p.qa[qs], p.ta[qs]), ("text", p.qt[qs], p.tt[qs])):
+                    if which == "text" or db.mode == "A":
+                        t = db.txt if which == "text" else db.aud
+                        _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm),
+                                                                 _lib.ptr(db.labels), t.W, t.D, db.id_offset, _lib.ptr(q),
+                                                                 S8, _lib.ptr(tab), 0, sp), "qpg_cand_cosine_minbycode")
+                    else:
+                        _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W,
+                                                              db.id_offset, _lib.ptr(q), S8, _lib.ptr(tab), sp),
+                                   "qpg_cand_lev_minbycode")
+                ev = torch.cuda.Event()
+                ev.record(main)
+                side.wait_event(ev)
+                with torch.cuda.stream(side):
+                    ss = _lib.stream_ptr(side)
+                    _lib.check(lib.qpg_rank512(_lib.ptr(p.ta[qs]), S8, _lib.ptr(p.ra[qs]), ss), "qpg_rank512")
+                    _lib.check(lib.qpg_rank512(_lib.ptr(p.tt[qs]), S8, _lib.ptr(p.rt[qs]), ss), "qpg_rank512")
+                    _lib.check(lib.qpg_match_tail_segments(
+                        _lib.ptr(p.ta), _lib.ptr(p.tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank),
+                        _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
+                        _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
+                        1, p.n_seg, g, 1, _lib.ptr(p.state), _lib.ptr(p.codes), _lib.ptr(p.vote), _lib.ptr(p.phase),
+                        _lib.ptr(p.status), ss), "qpg_match_tail_segments")
+        finally:
+            lib.qpg_tune_cosine(0, 0, 0, 0)
+        main.wait_stream(side)
+
     def _launch_plan(self, p):
+        if getattr(p, "overlap", False):
+            return self._launch_plan_overlapped(p)
         lib, db = _lib.load(), self.db
         sp = _lib.stream_ptr()
         for which, q, tab in (("audio", p.qa, p.ta), ("text", p.qt, p.tt)):

@@ -55,6 +55,8 @@ SIGNATURES = {
     "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),
     "qpg_rank512": (_INT, [_P, _INT, _P, _P]),
     "qpg_match_tail": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
+    "qpg_match_tail_segments": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _INT, _INT, _P,
+                                       _P, _P, _P, _P, _P]),
     "qpg_vq_argmin_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
     "qpg_vq_dequantise_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P]),
     "qpg_conv1d_taps_f32": (_INT, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(KB)
                       const int32_t* __restrict__ code, int64_t n_seq, const float* __restrict__ phase_amp,
                       const int32_t* __restrict__ aud_frame, const int32_t* __restrict__ txt_frame,
                       const int32_t* __restrict__ seed_code, const float* __restrict__ seed_phase, int n_seg,
+                      int seg_begin, int seg_count, float* __restrict__ state,
                       int64_t* __restrict__ codes_out, int32_t* __restrict__ vote_out,
                       float* __restrict__ phase_out, int32_t* __restrict__ status_out) {
   __shared__ float prev[8 * PC];
@@ -86,19 +87,28 @@ __global__ void __launch_bounds__(KB)
   __shared__ int s_fail;
 
   const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
-  if (c < 8 * PC) prev[c] = seed_phase[(size_t)b * 8 * PC + c];
+  // chained launches (one per segment) hand (last code, previous phase) over through `state`
+  float* st_b = state ? state + (size_t)b * (8 * PC + 4) : nullptr;
+  const bool resume = seg_begin > 0 && st_b != nullptr;
+  if (c < 8 * PC) prev[c] = resume ? st_b[4 + c] : seed_phase[(size_t)b * 8 * PC + c];
   if (c == 0) s_fail = 0;
-  int last = seed_code[b];
+  int last = resume ? __float_as_int(st_b[0]) : seed_code[b];
+  if (resume && __float_as_int(st_b[1]) != 0) {   // an earlier segment already failed
+    if (c == 0) status_out[b] = 1;
+    return;
+  }
   const double freq_term = __dmul_rn((double)freq_rank[c], 0.05);
-  const int n_steps = n_seg * 8;
-  const size_t q0 = (size_t)b * n_steps;
+  const int n_steps = (seg_begin + seg_count) * 8;
+  const int first_step = seg_begin * 8;
+  const size_t q0 = (size_t)b * n_seg * 8;
   // ranks and window ids of a step do not depend on the sequential state: keep one step in flight
-  int ra_n = aud_rank[q0 * KB + c], rt_n = txt_rank[q0 * KB + c];
-  long long ida_n = (long long)aud_table[q0 * KB + c].id, idt_n = (long long)txt_table[q0 * KB + c].id;
+  int ra_n = aud_rank[(q0 + first_step) * KB + c], rt_n = txt_rank[(q0 + first_step) * KB + c];
+  long long ida_n = (long long)aud_table[(q0 + first_step) * KB + c].id;
+  long long idt_n = (long long)txt_table[(q0 + first_step) * KB + c].id;
   __syncthreads();
 
   int code29 = last;
-  for (int st = 0; st < n_steps; ++st) {
+  for (int st = first_step; st < n_steps; ++st) {
     const int g = st >> 3, s = st & 7;
     const size_t q = q0 + st;
     const int ra = ra_n, rt = rt_n;
@@ -176,7 +186,10 @@ __global__ void __launch_bounds__(KB)
     }
     __syncthreads();
     if (s_fail) {
-      if (c == 0) status_out[b] = 1;
+      if (c == 0) {
+        status_out[b] = 1;
+        if (st_b) st_b[1] = __int_as_float(1);
+      }
       return;
     }
     const int final_idx = (s_dist[0] <= s_dist[1]) ? 0 : 1;  // tmp_distance.index(min(...)): audio wins ties
@@ -198,6 +211,13 @@ __global__ void __launch_bounds__(KB)
     __syncthreads();
   }
   if (c == 0) status_out[b] = 0;
+  if (st_b) {
+    if (c == 0) {
+      st_b[0] = __int_as_float(last);
+      st_b[1] = __int_as_float(0);
+    }
+    if (c < 8 * PC) st_b[4 + c] = prev[c];
+  }
 }
 
 }  // namespace
@@ -225,21 +245,46 @@ extern "C" int qpg_rank512(const qpg_pair_t* table, int Q, int32_t* ranks, void*
   return QPG_OK;
 }
 
+static int match_tail_launch(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, const int32_t* aud_rank,
+                             const int32_t* txt_rank, const int32_t* pos_rank, const int32_t* freq_rank,
+                             const int32_t* code, int64_t n_seq, const float* phase_amp, const int32_t* aud_frame,
+                             const int32_t* txt_frame, const int32_t* seed_code, const float* seed_phase, int n_clips,
+                             int n_seg, int seg_begin, int seg_count, float* state, int64_t* codes_out,
+                             int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream) {
+  QPG_CHECK_ARG(n_clips >= 0 && n_seg >= 0 && n_seq >= 0, "negative size");
+  QPG_CHECK_ARG(seg_begin >= 0 && seg_count >= 0 && seg_begin + seg_count <= n_seg, "segment range");
+  QPG_CHECK_ARG(seg_begin == 0 || state != nullptr, "resuming needs a state buffer");
+  if (n_clips == 0 || seg_count == 0) return QPG_OK;
+  QPG_CHECK_ARG(aud_table && txt_table && aud_rank && txt_rank && pos_rank && freq_rank && code && phase_amp &&
+                    aud_frame && txt_frame && seed_code && seed_phase && codes_out && vote_out && status_out,
+                "null pointer");
+  match_tail_kernel<<<n_clips, KB, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const Pair*>(aud_table), reinterpret_cast<const Pair*>(txt_table), aud_rank, txt_rank,
+      pos_rank, freq_rank, code, n_seq, phase_amp, aud_frame, txt_frame, seed_code, seed_phase, n_seg, seg_begin,
+      seg_count, state, codes_out, vote_out, phase_out, status_out);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
 extern "C" int qpg_match_tail(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, const int32_t* aud_rank,
                               const int32_t* txt_rank, const int32_t* pos_rank, const int32_t* freq_rank,
                               const int32_t* code, int64_t n_seq, const float* phase_amp, const int32_t* aud_frame,
                               const int32_t* txt_frame, const int32_t* seed_code, const float* seed_phase,
                               int n_clips, int n_seg, int64_t* codes_out, int32_t* vote_out, float* phase_out,
                               int32_t* status_out, void* stream) {
-  QPG_CHECK_ARG(n_clips >= 0 && n_seg >= 0 && n_seq >= 0, "negative size");
-  if (n_clips == 0 || n_seg == 0) return QPG_OK;
-  QPG_CHECK_ARG(aud_table && txt_table && aud_rank && txt_rank && pos_rank && freq_rank && code && phase_amp &&
-                    aud_frame && txt_frame && seed_code && seed_phase && codes_out && vote_out && status_out,
-                "null pointer");
-  match_tail_kernel<<<n_clips, KB, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const Pair*>(aud_table), reinterpret_cast<const Pair*>(txt_table), aud_rank, txt_rank,
-      pos_rank, freq_rank, code, n_seq, phase_amp, aud_frame, txt_frame, seed_code, seed_phase, n_seg, codes_out,
-      vote_out, phase_out, status_out);
-  QPG_LAUNCH_CHECK();
-  return QPG_OK;
+  return match_tail_launch(aud_table, txt_table, aud_rank, txt_rank, pos_rank, freq_rank, code, n_seq, phase_amp,
+                           aud_frame, txt_frame, seed_code, seed_phase, n_clips, n_seg, 0, n_seg, nullptr, codes_out,
+                           vote_out, phase_out, status_out, stream);
+}
+
+extern "C" int qpg_match_tail_segments(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table,
+                                       const int32_t* aud_rank, const int32_t* txt_rank, const int32_t* pos_rank,
+                                       const int32_t* freq_rank, const int32_t* code, int64_t n_seq,
+                                       const float* phase_amp, const int32_t* aud_frame, const int32_t* txt_frame,
+                                       const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg,
+                                       int seg_begin, int seg_count, float* state, int64_t* codes_out,
+                                       int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream) {
+  return match_tail_launch(aud_table, txt_table, aud_rank, txt_rank, pos_rank, freq_rank, code, n_seq, phase_amp,
+                           aud_frame, txt_frame, seed_code, seed_phase, n_clips, n_seg, seg_begin, seg_count, state,
+                           codes_out, vote_out, phase_out, status_out, stream);
 }

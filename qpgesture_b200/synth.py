@@ -112,3 +112,58 @@ def write_npz_set(root: str, train, test, code, signature, object_phase: bool = 
     np.savez(p.train_wavvq, wavvq=train["wavvq"])
     np.savez(p.test_wavvq, wavvq=test["wavvq"])
     return p
+
+
+# --------------------------------------------------------------------------------------------
+# VQ-VAE: there is no checkpoint to load, so tests and the bench use seeded random-init weights
+# in the reference's state-dict layout (codebook/models/*.py; keys as listed in DESIGN.md).
+# --------------------------------------------------------------------------------------------
+VQVAE_HPS = dict(levels=1, downs_t=[3], strides_t=[2], emb_width=512, l_bins=512, l_mu=0.99, commit=0.02,
+                 hvqvae_multipliers=[1], width=512, depth=3, m_conv=1.0, dilation_growth_rate=3,
+                 sample_length=30, use_bottleneck=True, joint_channel=9, vel=1, acc=1,
+                 vqvae_reverse_decoder_dilation=True)    # configs/codebook.yml:1-25
+
+
+def vqvae_hps(**over):
+    from types import SimpleNamespace
+    d = dict(VQVAE_HPS)
+    d.update(over)
+    return SimpleNamespace(**d)
+
+
+import torch  # noqa: E402
+
+
+def random_vqvae_state_dict(hps, input_dim=135, seed=0, codebook_seed=1, codebook_scale=0.12):
+    """Deterministic weights in the reference's state-dict layout (there is no
+    checkpoint to load): Conv default-style uniform(-1/sqrt(fan_in), ..) and a
+    N(0, codebook_scale^2) codebook (SURVEY.md 8(d) config 2 uses N(0,1); scaled here, see below)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+
+    def conv(name, cout, cin, k, transposed=False):
+        bound = 1.0 / (cin * k) ** 0.5
+        shape = (cin, cout, k) if transposed else (cout, cin, k)
+        sd[name + ".weight"] = (torch.rand(shape, generator=g) * 2 - 1) * bound
+        sd[name + ".bias"] = (torch.rand((cout,), generator=g) * 2 - 1) * bound
+
+    w, e, down_t = hps.width, hps.emb_width, hps.downs_t[0]
+    pre = "encoders.0.level_blocks.0.model"
+    for i in range(down_t):
+        conv(f"{pre}.{i}.0", w, input_dim if i == 0 else w, hps.strides_t[0] * 2)
+        for d in range(hps.depth):
+            conv(f"{pre}.{i}.1.model.{d}.model.1", w, w, 3)
+            conv(f"{pre}.{i}.1.model.{d}.model.3", w, w, 1)
+    conv(f"{pre}.{down_t}", e, w, 3)
+    pre = "decoders.0.level_blocks.0.model"
+    conv(f"{pre}.0", w, e, 3)
+    for i in range(down_t):
+        for d in range(hps.depth):
+            conv(f"{pre}.{i + 1}.0.model.{d}.model.1", w, w, 3)
+            conv(f"{pre}.{i + 1}.0.model.{d}.model.3", w, w, 1)
+        conv(f"{pre}.{i + 1}.1", e if i == down_t - 1 else w, w, hps.strides_t[0] * 2, transposed=True)
+    conv("decoders.0.out", input_dim, e, 3)
+    # scaled to the magnitude of the random-weight encoder's latents so that the arg-min is contested
+    sd["bottleneck.level_blocks.0.k"] = codebook_scale * torch.randn(
+        (hps.l_bins, e), generator=torch.Generator().manual_seed(codebook_seed))
+    return sd
