@@ -47,6 +47,8 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=("ours", "reference"), default="ours")
+    p.add_argument("--workload", choices=("speaker10_24s", "allspeaker"), default="speaker10_24s",
+                   help="allspeaker: 32 768 sequences (852k windows, 22 GB) generated on the device, 8 clips, strong scaling")
     p.add_argument("--n-seq", type=int, default=512)
     p.add_argument("--wavlm-dim", type=int, default=1024)
     p.add_argument("--ctx-dim", type=int, default=384)
@@ -72,6 +74,26 @@ def make_database_arrays(n_seq, wavlm_dim, ctx_dim, seed=0):
     txt_rows = np.ascontiguousarray(train["context"].squeeze(2)[:, :26, :].reshape(n_seq * 26, -1))
     return dict(code=code, signature=sig, phase_amp=phase_to_dense(train["phase"]), aud_rows=aud_rows,
                 txt_rows=txt_rows, train=train)
+
+
+def make_database_on_device(n_seq, wavlm_dim, ctx_dim, j0, j1, dev, block=512):
+    """Large synthetic database generated on the GPU in 512-sequence blocks whose content depends only on
+    the block index, so every shard layout sees the same table.  Returns (small host arrays, audio rows of
+    sequences [j0, j1) on the device, text rows on the device)."""
+    import torch
+
+    rng = np.random.default_rng(0)
+    code = rng.integers(0, 512, size=(n_seq, 30)).astype(np.int64)
+    signature = rng.standard_normal((512, 135)).astype(np.float32)
+    phase_amp = rng.standard_normal((n_seq, 240, 16)).astype(np.float32)
+    assert j0 % block == 0 and j1 % block == 0, "shards must be multiples of 512 sequences"
+    aud, txt = [], []
+    g = torch.Generator(device=dev)
+    for blk in range(j0 // block, j1 // block):
+        g.manual_seed(1000 + blk)
+        aud.append(torch.randn((block * 26, 6 * wavlm_dim), device=dev, generator=g))
+        txt.append(torch.randn((block * 26, ctx_dim), device=dev, generator=g))
+    return dict(code=code, signature=signature, phase_amp=phase_amp), torch.cat(aud), torch.cat(txt)
 
 
 def make_clip_queries(n_clips, wavlm_dim, ctx_dim, seed=1000):
@@ -253,11 +275,14 @@ def main():
     pg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
     # ---- layout: row shards x clip groups (qpgesture_b200/sharding.py: never cut a shard below the L2 size)
     from qpgesture_b200.sharding import plan_layout, shard_sequences
+    if args.workload == "allspeaker" and args.n_seq == 512:
+        args.n_seq = 32768
     db_bytes_total = args.n_seq * 26 * 4 * (6 * args.wavlm_dim + args.ctx_dim)
     row_shards, clip_groups = plan_layout(db_bytes_total, world) if args.row_shards == 0 else \
         (args.row_shards, world // args.row_shards)
@@ -272,12 +297,23 @@ def main():
         pg = None
 
     # ---- database (one-off, outside every timed region)
-    arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
     j0, j1 = shard_sequences(args.n_seq, row_shards, my_block)
-    db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
-                       aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
+    if args.workload == "allspeaker":
+        arrs, aud_dev, txt_dev = make_database_on_device(args.n_seq, args.wavlm_dim, args.ctx_dim, j0, j1, dev)
+        db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], txt_dev, aud_rows=aud_dev,
+                           device=dev, seq_range=(j0, j1))
+        del aud_dev, txt_dev
+        torch.cuda.empty_cache()
+    else:
+        arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
+        db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
+                           aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
     knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg)
-    n_clips_total = args.clips_per_gpu * world
+    strong = args.workload == "allspeaker"                 # fixed total work: 8 clips however many GPUs
+    n_clips_total = 8 if strong else args.clips_per_gpu * world
+    if strong:
+        assert n_clips_total % clip_groups == 0 and (n_clips_total // clip_groups) % row_shards == 0
+        args.clips_per_gpu = n_clips_total // world
     n_clips = args.clips_per_gpu * row_shards              # clips this rank's row group scans together
     aq_all, tq_all, _, _ = make_clip_queries(n_clips_total, args.wavlm_dim, args.ctx_dim)
     g_lo = my_group * n_clips
@@ -410,8 +446,8 @@ def main():
         line = dict(
             metric="seconds_of_audio_matched_per_second", value=audio_seconds / (ms_res * 1e-3), unit="s_audio/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
-            scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
+            scaling="strong" if strong else "weak", vs_baseline=None, dtype="f64", data="synthetic",
+            config=dict(workload=args.workload, n_seq=args.n_seq, windows=args.n_seq * 26,
                         audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph), tail_overlapped=bool(plan.overlap),
                         query_steps_per_rank_per_step=Q, db_bytes=int(db_bytes_total),
                         parallelism=(f"{row_shards} row shards x {clip_groups} clip groups"

@@ -177,13 +177,18 @@ class MatchDatabase:
         assert self.phase_amp_host.shape == (self.n_seq, num_frames, 16)
         self.phase_amp = torch.from_numpy(self.phase_amp_host).to(dev)
 
-        txt = np.ascontiguousarray(np.asarray(txt_rows, dtype=np.float32)[w0:w1])
-        self.txt = PackedRows.from_rows(torch.from_numpy(txt).to(dev))
+        def local_rows(rows):
+            """host array of ALL windows (sliced to this shard here) or a CUDA tensor holding this shard only"""
+            if isinstance(rows, torch.Tensor):
+                assert rows.is_cuda and rows.shape[0] == self.W, "device rows must be this rank's shard"
+                return rows.to(device=dev, dtype=torch.float32)
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float32)[w0:w1])).to(dev)
+
+        self.txt = PackedRows.from_rows(local_rows(txt_rows))
         self.aud = None
         self.tokens = None
         if mode == "A":
-            aud = np.ascontiguousarray(np.asarray(aud_rows)[w0:w1], dtype=np.float32)
-            self.aud = PackedRows.from_rows(torch.from_numpy(aud).to(dev))
+            self.aud = PackedRows.from_rows(local_rows(aud_rows))
             self.aud_k = [m * 6 for m in range(WINDOWS_PER_SEQ)]                    # k = 0,6,...,150
             self.n_db_frm, self.step_sz = 180, 6
         else:
