@@ -273,9 +273,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     pg = None
+    json_fd = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
+        # NCCL writes its version banner to stdout; the driver wants exactly ONE JSON line there.
+        # Point fd 1 at stderr for the whole run and keep the real stdout for the final line.
+        sys.stdout.flush()
+        json_fd = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
 
@@ -470,7 +475,10 @@ def main():
             line["vqvae"] = vqvae_block(dev)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
-        print(json.dumps(line))
+        if json_fd is not None:
+            os.write(json_fd, (json.dumps(line) + "\n").encode())
+        else:
+            print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
         # Tear down without touching the NCCL communicator that the captured graph references:
