@@ -510,11 +510,14 @@ class CodeKNN(object):
                                         desired_k, use_txt=use_txt, use_aud=use_aud)
 
     # ---- batched entry: many clips at once ---------------------------------------
-    def match_clips(self, aud_q, txt_q, seed_code=None, seed_phase=None, tail=None):
-        """aud_q [n_clips, n_seg, 8, Da] (or tokens [..., 11|22]), txt_q [n_clips, n_seg, 8, Dt]
-        (host arrays).  Returns int64 codes [n_clips, n_seg, 30] on the host."""
+    def match_clips(self, aud_q, txt_q, seed_code=None, seed_phase=None, tail=None, out=None, sync=True,
+                    tail_clips=None):
+        """aud_q [n_clips, n_seg, 8, Da] (or tokens [..., 11|22]), txt_q [n_clips, n_seg, 8, Dt]: host NumPy
+        arrays or (pinned) host torch tensors.  Returns int64 codes [n_clips, n_seg, 30] on the host.
+        With `out` (a pinned int64 host tensor) and sync=False the call only enqueues H2D copies, the
+        captured step and the D2H copy on the current stream (the caller synchronises)."""
         tail = tail or self.tail
-        aud_q, txt_q = np.asarray(aud_q), np.asarray(txt_q)
+        is_t = isinstance(aud_q, torch.Tensor)
         n_clips, n_seg = aud_q.shape[0], aud_q.shape[1]
         Q = n_clips * n_seg * STEPS_PER_SEGMENT
         if seed_code is None:
@@ -522,24 +525,40 @@ class CodeKNN(object):
             seed_code = [s[0] for s in seeds]
             seed_phase = np.stack([s[1] for s in seeds])
         if tail == "device":
-            key = (n_clips, n_seg)
+            key = (n_clips, n_seg, None if tail_clips is None else (tail_clips.start, tail_clips.stop))
             plans = self.__dict__.setdefault("_plans", {})
             if key not in plans:
-                plans[key] = self.make_plan(n_clips, n_seg, use_graph=self.process_group is None)
+                plans[key] = self.make_plan(n_clips, n_seg, tail_clips=tail_clips)
             p = plans[key]
             dev = self.db.device
             with torch.cuda.device(dev):
-                p.qa.copy_(self._audio_query_tensor(aud_q.reshape((Q,) + aud_q.shape[3:])), non_blocking=True)
-                p.qt.copy_(torch.from_numpy(np.ascontiguousarray(txt_q.reshape(Q, -1), dtype=np.float32)),
-                           non_blocking=True)
-                p.seed_code.copy_(torch.from_numpy(np.asarray(seed_code, dtype=np.int32).reshape(n_clips)))
-                p.seed_phase.copy_(torch.from_numpy(np.ascontiguousarray(seed_phase, dtype=np.float32)
-                                                    .reshape(n_clips, 8, 16)))
+                if is_t:
+                    qa_h, qt_h = aud_q.reshape(Q, -1), txt_q.reshape(Q, -1)
+                else:
+                    aud_q, txt_q = np.asarray(aud_q), np.asarray(txt_q)
+                    qa_h = self._audio_query_tensor(aud_q.reshape((Q,) + aud_q.shape[3:]))
+                    qt_h = torch.from_numpy(np.ascontiguousarray(txt_q.reshape(Q, -1), dtype=np.float32))
+                sc_h = seed_code if isinstance(seed_code, torch.Tensor) else \
+                    torch.from_numpy(np.asarray(seed_code, dtype=np.int32).reshape(n_clips))
+                sp_h = seed_phase if isinstance(seed_phase, torch.Tensor) else \
+                    torch.from_numpy(np.ascontiguousarray(seed_phase, dtype=np.float32).reshape(n_clips, 8, 16))
+                p.qa.copy_(qa_h, non_blocking=True)
+                p.qt.copy_(qt_h, non_blocking=True)
+                p.seed_code.copy_(sc_h, non_blocking=True)
+                p.seed_phase.copy_(sp_h, non_blocking=True)
                 self.run_plan(p)
-                codes_h = p.codes.cpu().numpy()
+                if out is not None:
+                    out.copy_(p.codes, non_blocking=True)
+                    if not sync:
+                        return out
+                    torch.cuda.synchronize(dev)
+                    codes_h = out.numpy()
+                else:
+                    codes_h = p.codes.cpu().numpy()
                 if int(p.status.max().cpu()) != 0:
                     raise IndexError("list index out of range")
             return codes_h
+        aud_q, txt_q = np.asarray(aud_q), np.asarray(txt_q)
         ta, tt = self.match_tables(aud_q.reshape((Q,) + aud_q.shape[3:]), txt_q.reshape(Q, -1))
         ta_np = table_to_numpy(ta).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)
         tt_np = table_to_numpy(tt).reshape(n_clips, n_seg, STEPS_PER_SEGMENT, codebook_size)

@@ -226,6 +226,32 @@ class MatchDatabase:
         return [j, int((self.aud_k if which == "audio" else self.txt_k)[m])]
 
 
+def save_packed_db(path: str, mode: str, code, signature, phase_amp, txt_rows, aud_rows=None, aud_tokens=None,
+                   freq_code=None) -> None:
+    """Row 8(f).1: one-file database for the matcher.  Everything load_db_codebook + CodeKNN.__init__ derive at
+    start-up in the reference (stacked window rows, dense phase|amplitude, frequency and pose rank tables) is
+    stored ready to upload; `load_packed_db` rebuilds a MatchDatabase without touching the raw npz set."""
+    code = np.asarray(code)
+    rec = dict(mode=np.array(mode), code=code, signature=np.asarray(signature, dtype=np.float32),
+               phase_amp=np.asarray(phase_amp, dtype=np.float32), txt_rows=np.asarray(txt_rows, dtype=np.float32),
+               freq_rank=freq_rank_from_code(code if freq_code is None else freq_code),
+               pos_rank=pos_rank_table(np.asarray(signature)))
+    if mode == "A":
+        rec["aud_rows"] = np.asarray(aud_rows, dtype=np.float32)
+    else:
+        rec["aud_tokens"] = np.asarray(aud_tokens, dtype=np.int64)
+    np.savez(path, **rec)
+
+
+def load_packed_db(path: str, device=None, seq_range=None) -> "MatchDatabase":
+    z = np.load(path)
+    mode = str(z["mode"])
+    return MatchDatabase(mode, z["code"], z["signature"], z["phase_amp"], z["txt_rows"],
+                         aud_rows=z["aud_rows"] if mode == "A" else None,
+                         aud_tokens=z["aud_tokens"] if mode == "B" else None, freq_rank=z["freq_rank"],
+                         pos_rank=z["pos_rank"], device=device, seq_range=seq_range)
+
+
 def new_table(Q: int, device) -> torch.Tensor:
     """Uninitialised [Q, 512] table of qpg_pair_t (stored as int64 [Q,512,2])."""
     return torch.empty((Q, codebook_size, 2), dtype=torch.int64, device=device)

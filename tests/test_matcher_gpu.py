@@ -388,3 +388,26 @@ def test_full_size_speaker10_properties():
         (bd, bw), _ = _oracle_cosine_table(rows_h, lab_h, q[qi].cpu().numpy())
         assert np.array_equal(full[qi]["id"], bw)
         assert np.allclose(full[qi]["d"], bd, rtol=0, atol=1e-12)
+
+
+def test_packed_db_roundtrip(tmp_path):
+    """Row 8(f).1: save_packed_db / load_packed_db reproduce the matcher's output without the raw npz set."""
+    from qpgesture_b200 import data_processing as dp
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import load_packed_db, phase_to_dense, save_packed_db
+
+    fx, train, test, code, sig = load_case(CASES[0])
+    n = code.shape[0]
+    txt_rows = train["context"].squeeze(2)[:, :26, :].reshape(n * 26, -1)
+    aud_rows = dp.wavlm_window_rows(dp.interpolate_wavlm(train["wavlm"]))
+    path = str(tmp_path / "db.npz")
+    save_packed_db(path, "A", code, sig, phase_to_dense(train["phase"]), txt_rows, aud_rows=aud_rows)
+    db = load_packed_db(path)
+    db.freq_rank_host[:] = fx["freq_rank"]                      # fixture carries the recorded tie order
+    db.freq_rank.copy_(_torch().from_numpy(fx["freq_rank"].astype(np.int32)))
+    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True)
+    aq = dp.wavlm_query_rows(dp.interpolate_wavlm(test["wavlm"]))
+    tq = test["context"].squeeze(2)[:, [int(24 * s / 180 * 30) for s in range(8)], :]
+    np.random.seed(123456)
+    got = knn.match_clips(aq[None], tq[None])[0]
+    assert np.array_equal(got, fx["knn_pred"])
