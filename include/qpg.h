@@ -56,6 +56,9 @@ const char* qpg_last_error(void);
 uint64_t qpg_launch_count(void);
 /* tuning hook for sweeps (0 = automatic): compute warps per CTA (8|12), ring depth, grid size, team size */
 int qpg_tune_cosine(int compute_warps, int stages, int grid, int team);
+/* consecutive passes of one scan call walk the row groups in alternating direction (default on) so that a
+ * pass starts on the part of the table its predecessor left in L2; results do not depend on it */
+int qpg_tune_cosine_alternate(int enable);
 
 /* ---------------- packed window database ---------------------------------
  * Row-major float32 windows [W, D] are re-laid-out once per database into

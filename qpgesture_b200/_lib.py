@@ -45,6 +45,7 @@ SIGNATURES = {
     "qpg_last_error": (C.c_char_p, []),
     "qpg_launch_count": (C.c_uint64, []),
     "qpg_tune_cosine": (_INT, [_INT, _INT, _INT, _INT]),
+    "qpg_tune_cosine_alternate": (_INT, [_INT]),
     "qpg_packed_bytes": (C.c_size_t, [_I64, _INT]),
     "qpg_pack_rows_f32": (_INT, [_P, _I64, _INT, _P, _P, _P]),
     "qpg_table_init": (_INT, [_P, _I64, _P]),

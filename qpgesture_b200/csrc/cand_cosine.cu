@@ -96,6 +96,17 @@ struct TransposeReduce {
   }
 };
 
+// Exact float32 -> float64 conversion on the integer ALU (normal numbers: re-bias the exponent, move the
+// mantissa); zero / denormal / inf / nan take the F2F path.  Used for the query operands so that the XU pipe
+// (F2F.F64.F32 runs there at 1/8 rate) only converts the database elements.
+__device__ __forceinline__ double f32_to_f64_alu(float f) {
+  const uint32_t u = __float_as_uint(f);
+  const uint32_t e = u & 0x7f800000u;
+  if (e == 0u || e == 0x7f800000u) return (double)f;
+  const uint32_t hi = (u & 0x80000000u) | (((u & 0x7fffffffu) >> 3) + 0x38000000u);
+  return __hiloint2double((int)hi, (int)(u << 29));
+}
+
 __device__ __forceinline__ double cosine_distance(double dot, double sqq, double sqx) {
   // sklearn: normalize() leaves an all-zero vector at zero (norm 0 -> 1), then
   // 0.5*||a-b||^2 = 0.5*(|a|^2+|b|^2) - <a,b> with |a|,|b| in {0,1}.
@@ -108,6 +119,14 @@ __device__ __forceinline__ double cosine_distance(double dot, double sqq, double
 }
 
 // ------------------------------------------------------------ main kernel ----
+#ifndef QPG_QCVT_ALU
+#define QPG_QCVT_ALU 0  // measured: ALU-side conversion is slower (66.0 vs 61.5 us at D=6144, 511 vs 364 us on 1Mx512)
+#endif
+#if QPG_QCVT_ALU
+#define QPG_QCVT(x) f32_to_f64_alu(x)
+#else
+#define QPG_QCVT(x) ((double)(x))
+#endif
 constexpr int MAXNS = 4;  // ring depth cap per warp (mbarriers are allocated for this many)
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -126,7 +145,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
     cand_cosine_kernel(const float* __restrict__ packed, const double* __restrict__ row_sqnorm,
                        const int32_t* __restrict__ labels, int64_t W, int D, int NC, int64_t G,
                        int64_t id_offset, const float* __restrict__ q, int nq, Pair* __restrict__ table,
-                       int pool_tiles, int S) {
+                       int pool_tiles, int S, int reverse) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   constexpr int PER_LANE = (R * QT >= 32) ? (R * QT) / 32 : 1;
   constexpr int DUP = (R * QT >= 32) ? 1 : 32 / (R * QT);  // lanes holding the same total
@@ -171,8 +190,13 @@ __global__ void __launch_bounds__(NCW * 32, 1)
   float* my_ring = ring + (size_t)busy_rank * NS * TILE_FLOATS;
   uint64_t* my_bars = bars + warp * MAXNS;
 
-  // prefetch cursor (pg, pc) runs NS tiles ahead of the consume cursor (g, c)
-  int64_t pg = g0;
+  // prefetch cursor (pg, pc) runs NS tiles ahead of the consume cursor (g, c).  With `reverse` the
+  // team walks its row groups from last to first (chunk order inside a group never changes, so the
+  // summation order of a dot product is the same): consecutive passes alternate direction and the
+  // second one starts on the part of the table the first one left in L2.
+  const int64_t gstep = reverse ? -1 : 1;
+  const int64_t gfirst = reverse ? g1 - 1 : g0;
+  int64_t pg = gfirst;
   int pc = c_lo;
   int64_t issued = 0;
   if (lane == 0) {
@@ -182,7 +206,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
                &my_bars[s]);
       if (++pc == c_hi) {
         pc = c_lo;
-        ++pg;
+        pg += gstep;
       }
     }
   }
@@ -231,7 +255,8 @@ __global__ void __launch_bounds__(NCW * 32, 1)
   double* team_part = part + (size_t)team * (S - 1) * (PER_LANE * 32);
   int s = 0, c = c_lo;
   uint32_t parity = 0;
-  int64_t g = g0;
+  int64_t g = gfirst;
+  int64_t g_done = 0;
   // a member without chunks (NC < S) still takes part in the team protocol once per group
   const int64_t n_iter = ncs > 0 ? n_tiles : n_groups;
   for (int64_t it = 0; it < n_iter; ++it) {
@@ -251,7 +276,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
         double qd[QT];
 #pragma unroll
         for (int qi = 0; qi < QT; ++qi)
-          qd[qi] = (double)(comp == 0 ? qv[qi].x : comp == 1 ? qv[qi].y : comp == 2 ? qv[qi].z : qv[qi].w);
+          qd[qi] = QPG_QCVT(comp == 0 ? qv[qi].x : comp == 1 ? qv[qi].y : comp == 2 ? qv[qi].z : qv[qi].w);
 #pragma unroll
         for (int r = 0; r < R; ++r) {
           const double xd = (double)(comp == 0 ? x[r].x : comp == 1 ? x[r].y : comp == 2 ? x[r].z : x[r].w);
@@ -270,7 +295,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
         ++issued;
         if (++pc == c_hi) {
           pc = c_lo;
-          ++pg;
+          pg += gstep;
         }
       }
       if (++s == NS) {
@@ -285,7 +310,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
     TransposeReduce<R * QT, 16>::run(acc, lane);
     if (S > 1) {
       if (member > 0) {
-        if (g > g0) named_bar_sync(bar_b, S * 32);  // member 0 has consumed the previous partials
+        if (g_done > 0) named_bar_sync(bar_b, S * 32);  // member 0 has consumed the previous partials
 #pragma unroll
         for (int j = 0; j < PER_LANE; ++j) team_part[(size_t)(member - 1) * (PER_LANE * 32) + j * 32 + lane] = acc[j];
         named_bar_arrive(bar_a, S * 32);
@@ -295,7 +320,7 @@ __global__ void __launch_bounds__(NCW * 32, 1)
 #pragma unroll
           for (int j = 0; j < PER_LANE; ++j) acc[j] += team_part[(size_t)(m - 1) * (PER_LANE * 32) + j * 32 + lane];
         }
-        if (g + 1 < g1) named_bar_arrive(bar_b, S * 32);
+        if (g_done + 1 < n_groups) named_bar_arrive(bar_b, S * 32);
       }
     }
     if (member == 0) {
@@ -324,7 +349,8 @@ __global__ void __launch_bounds__(NCW * 32, 1)
     }
 #pragma unroll
     for (int i = 0; i < R * QT; ++i) acc[i] = 0.0;
-    ++g;
+    g += gstep;
+    ++g_done;
   }
 
   // ---- merge the CTA table into the global one
@@ -340,6 +366,7 @@ struct Tuning {
   int ns = 0;
   int grid = 0;
   int team = 0;
+  int alternate = 1;  // alternate the walk direction between consecutive passes
 };
 Tuning g_tuning;
 
@@ -354,19 +381,24 @@ size_t fixed_smem(int QT, int D, int ncw, int S) {
 template <int QT, int NCW>
 int launch_cosine(const float* packed, const double* row_sqnorm, const int32_t* labels, int64_t W, int D,
                   int64_t id_offset, const float* q, int nq, Pair* table, int pool_tiles, int S, int grid,
-                  cudaStream_t st) {
+                  int reverse, cudaStream_t st) {
   const int NC = (D + DC - 1) / DC;
   const int64_t G = (W + R - 1) / R;
   const size_t smem = (size_t)pool_tiles * TILE_BYTES + fixed_smem(QT, D, NCW, S);
   auto kern = cand_cosine_kernel<QT, NCW>;
   QPG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   kern<<<grid, NCW * 32, smem, st>>>(packed, row_sqnorm, labels, W, D, NC, G, id_offset, q, nq, table, pool_tiles,
-                                     S);
+                                     S, reverse);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
 
 }  // namespace
+
+int cosine_set_alternate(int on) {
+  g_tuning.alternate = on ? 1 : 0;
+  return QPG_OK;
+}
 
 int cosine_set_tuning(int ncw, int ns, int grid, int team) {
   g_tuning.ncw = ncw;
@@ -475,9 +507,10 @@ static int cosine_scan(const float* packed, const double* row_sqnorm, const int3
     const int nq = (Q - q0) < qt ? (Q - q0) : qt;
     const float* qp = q + (size_t)q0 * D;
     Pair* tp = tab + (size_t)q0 * KB;
+    const int rev = (g_tuning.alternate && ((q0 / qt) & 1)) ? 1 : 0;
     int rc;
 #define QPG_DISPATCH(QT_, NCW_)                                                                              \
-  rc = launch_cosine<QT_, NCW_>(packed, row_sqnorm, labels, W, D, id_offset, qp, nq, tp, pool, S, grid, st)
+  rc = launch_cosine<QT_, NCW_>(packed, row_sqnorm, labels, W, D, id_offset, qp, nq, tp, pool, S, grid, rev, st)
     if (qt == 8) QPG_DISPATCH(8, 8);
     else if (qt == 4 && ncw == 12) QPG_DISPATCH(4, 12);
     else if (qt == 4) QPG_DISPATCH(4, 8);

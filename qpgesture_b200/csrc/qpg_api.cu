@@ -32,6 +32,7 @@ int sm_count() {
 }
 
 int cosine_set_tuning(int ncw, int ns, int grid, int team);
+int cosine_set_alternate(int on);
 
 }  // namespace qpg
 
@@ -45,3 +46,5 @@ extern "C" uint64_t qpg_launch_count(void) { return qpg::g_launches.load(std::me
 extern "C" int qpg_tune_cosine(int compute_warps, int stages, int grid, int team) {
   return qpg::cosine_set_tuning(compute_warps, stages, grid, team);
 }
+
+extern "C" int qpg_tune_cosine_alternate(int enable) { return qpg::cosine_set_alternate(enable); }
