@@ -58,6 +58,7 @@ def parse():
     p.add_argument("--row-shards", type=int, default=0, help="0 = plan_layout() decides")
     p.add_argument("--no-vqvae", action="store_true", help="skip the informational VQ-VAE block")
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    p.add_argument("--no-fused", action="store_true", help="separate audio and text scans instead of the fused pass")
     p.add_argument("--no-overlap", action="store_true", help="do not overlap the sequential tail with the scans")
     return p.parse_args()
 
@@ -345,12 +346,12 @@ def main():
     use_graph = not args.no_graph
     try:
         plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph,
-                             overlap_tail=not args.no_overlap)
+                             overlap_tail=not args.no_overlap, fused_scan=not args.no_fused)
     except Exception as e:                                   # e.g. NCCL capture unsupported: plain launches
         if rank == 0:
             print(f"[bench] graph capture failed ({type(e).__name__}: {e}); using plain launches", file=sys.stderr)
         use_graph = False
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=not args.no_overlap)
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=not args.no_overlap, fused_scan=not args.no_fused)
     knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, (my_clips.start, my_clips.stop))] = plan
     plan.qa.copy_(aq_h)
     plan.qt.copy_(tq_h)
@@ -453,7 +454,7 @@ def main():
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
             scaling="strong" if strong else "weak", vs_baseline=None, dtype="f64", data="synthetic",
             config=dict(workload=args.workload, n_seq=args.n_seq, windows=args.n_seq * 26,
-                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph), tail_overlapped=bool(plan.overlap),
+                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph), tail_overlapped=bool(plan.overlap), fused_text_scan=bool(plan.fused),
                         query_steps_per_rank_per_step=Q, db_bytes=int(db_bytes_total),
                         parallelism=(f"{row_shards} row shards x {clip_groups} clip groups"
                                      + (", all-gather + min-merge inside each row group" if row_shards > 1 else

@@ -97,6 +97,14 @@ int qpg_cand_cosine_minbycode_team(const float* packed, const double* row_sqnorm
                                    int64_t W, int D, int64_t id_offset, const float* q, int Q,
                                    qpg_pair_t* table, int queries_per_pass, int team_size, void* stream);
 
+/* Fused variant: rows carry two feature blocks [D1 | D2] (both multiples of 128 floats, packed as ONE
+ * table with qpg_pack_rows_f32 over D1+D2 columns); q is [Q, D1+D2].  One pass produces both tables:
+ * table1 from the first block (row_sqnorm1), table2 from the second (row_sqnorm2).  Replaces one
+ * search_audio_cands + one search_text_cands call per query step (GestureKNN.py:549-566). */
+int qpg_cand_cosine2_minbycode(const float* packed, const double* row_sqnorm1, const double* row_sqnorm2,
+                               const int32_t* labels, int64_t W, int D1, int D2, int64_t id_offset,
+                               const float* q, int Q, qpg_pair_t* table1, qpg_pair_t* table2, void* stream);
+
 /* ---------------- candidate distance, Levenshtein, fused min-by-code -----
  * tokens [W, 12] uint32 (11 used: g0*320+g1 per tap, GestureKNN.py:58-60),
  * q_tokens [Q, 12].  dist = unit-cost edit distance (Levenshtein.distance,

@@ -278,7 +278,7 @@ class CodeKNN(object):
 
     # ---- preallocated plan: the whole step as a fixed launch sequence (optionally one CUDA graph) ------
     def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False,
-                  overlap_tail: bool = True):
+                  overlap_tail: bool = True, fused_scan: bool = True):
         """Static device buffers for `n_clips` clips x `n_seg` segments.  `tail_clips` = slice of the
         clips whose sequential tail this rank runs (default: all).  Fill plan.qa / plan.qt /
         plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes."""
@@ -292,11 +292,19 @@ class CodeKNN(object):
         with torch.cuda.device(dev):
             p.side_stream = torch.cuda.Stream(device=dev) if p.overlap else None
             p.state = torch.zeros((max(n_tail, 1), 8 * 16 + 4), dtype=torch.float32, device=dev)
-            if db.mode == "A":
+            # fused single-pass scan when the audio|text table exists and a warp team split is not needed
+            sms = torch.cuda.get_device_properties(dev).multi_processor_count
+            p.fused = (db.fused is not None and self.process_group is None and fused_scan
+                       and -(-db.W // 8) * 2 >= sms * 12)
+            if p.fused:
+                p.qf = torch.zeros((Q, db.aud.D + db.txt.D), dtype=torch.float32, device=dev)
+                p.qa, p.qt = p.qf[:, :db.aud.D], p.qf[:, db.aud.D:]          # views: copy destinations only
+            elif db.mode == "A":
                 p.qa = torch.zeros((Q, db.aud.D), dtype=torch.float32, device=dev)
+                p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
             else:
                 p.qa = torch.zeros((Q, 12), dtype=torch.int32, device=dev)
-            p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
+                p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
             p.seed_code = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
             p.seed_phase = torch.zeros((n_clips, 8, 16), dtype=torch.float32, device=dev)
             p.ta, p.tt = new_table(Q, dev), new_table(Q, dev)
@@ -323,6 +331,12 @@ class CodeKNN(object):
                 p.graph = g
         return p
 
+    def _scan_fused(self, q, ta, tt, nq, sp):
+        lib, db = _lib.load(), self.db
+        _lib.check(lib.qpg_cand_cosine2_minbycode(_lib.ptr(db.fused.packed), _lib.ptr(db.aud.sqnorm), _lib.ptr(db.txt.sqnorm),
+                                                  _lib.ptr(db.labels), db.W, db.aud.D, db.txt.D, db.id_offset, _lib.ptr(q),
+                                                  nq, _lib.ptr(ta), _lib.ptr(tt), sp), "qpg_cand_cosine2_minbycode")
+
     def _launch_plan_overlapped(self, p):
         """Single clip, single GPU: segment g's ranks + tail run on a side stream (one SM is left free for
         them) while the main stream already scans segment g+1.  Same kernels, same results."""
@@ -338,7 +352,10 @@ class CodeKNN(object):
         try:
             for g in range(p.n_seg):
                 qs = slice(g * S8, (g + 1) * S8)
-                for which, q, tab in (("audio", p.qa[qs], p.ta[qs]), ("text", p.qt[qs], p.tt[qs])):
+                scans = () if p.fused else (("audio", p.qa[qs], p.ta[qs]), ("text", p.qt[qs], p.tt[qs]))
+                if p.fused:
+                    self._scan_fused(p.qf[qs], p.ta[qs], p.tt[qs], S8, sp)
+                for which, q, tab in scans:
                     if which == "text" or db.mode == "A":
                         t = db.txt if which == "text" else db.aud
                         _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm),
@@ -370,7 +387,11 @@ class CodeKNN(object):
             return self._launch_plan_overlapped(p)
         lib, db = _lib.load(), self.db
         sp = _lib.stream_ptr()
-        for which, q, tab in (("audio", p.qa, p.ta), ("text", p.qt, p.tt)):
+        if p.fused:
+            _lib.check(lib.qpg_table_init(_lib.ptr(p.ta), p.Q * codebook_size, sp), "qpg_table_init")
+            _lib.check(lib.qpg_table_init(_lib.ptr(p.tt), p.Q * codebook_size, sp), "qpg_table_init")
+            self._scan_fused(p.qf, p.ta, p.tt, p.Q, sp)
+        for which, q, tab in (() if p.fused else (("audio", p.qa, p.ta), ("text", p.qt, p.tt))):
             _lib.check(lib.qpg_table_init(_lib.ptr(tab), p.Q * codebook_size, sp), "qpg_table_init")
             if which == "text" or db.mode == "A":
                 t = db.txt if which == "text" else db.aud

@@ -51,6 +51,7 @@ SIGNATURES = {
     "qpg_table_init": (_INT, [_P, _I64, _P]),
     "qpg_cand_cosine_minbycode": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _P]),
     "qpg_cand_cosine_minbycode_team": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _INT, _P]),
+    "qpg_cand_cosine2_minbycode": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _I64, _P, _INT, _P, _P, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
     "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),

@@ -151,7 +151,7 @@ class MatchDatabase:
                  txt_rows: np.ndarray, aud_rows: Optional[np.ndarray] = None,
                  aud_tokens: Optional[np.ndarray] = None, freq_code: Optional[np.ndarray] = None,
                  freq_rank: Optional[np.ndarray] = None, pos_rank: Optional[np.ndarray] = None,
-                 device=None, seq_range=None):
+                 device=None, seq_range=None, fuse_text=True):
         """aud_rows [N*26, Da] float32 (mode A) or aud_tokens [N*26, 11] ints (mode B);
         txt_rows [N*26, Dt] float32.  `seq_range=(j0, j1)` keeps only the windows of
         sequences j0..j1-1 on this GPU (row shard); code / phase tables stay whole."""
@@ -184,11 +184,20 @@ class MatchDatabase:
                 return rows.to(device=dev, dtype=torch.float32)
             return torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float32)[w0:w1])).to(dev)
 
-        self.txt = PackedRows.from_rows(local_rows(txt_rows))
+        txt_dev = local_rows(txt_rows)
+        self.txt = PackedRows.from_rows(txt_dev)
         self.aud = None
         self.tokens = None
+        self.fused = None
         if mode == "A":
-            self.aud = PackedRows.from_rows(local_rows(aud_rows))
+            aud_dev = local_rows(aud_rows)
+            self.aud = PackedRows.from_rows(aud_dev)
+            # audio | text in one table for the fused single-pass scan (qpg_cand_cosine2_minbycode)
+            if fuse_text and aud_dev.shape[1] % 128 == 0 and txt_dev.shape[1] % 128 == 0 and \
+                    self.W * 4 * (aud_dev.shape[1] + txt_dev.shape[1]) <= (8 << 30):
+                self.fused = PackedRows.from_rows(torch.cat((aud_dev, txt_dev), dim=1))
+            del aud_dev
+        del txt_dev
             self.aud_k = [m * 6 for m in range(WINDOWS_PER_SEQ)]                    # k = 0,6,...,150
             self.n_db_frm, self.step_sz = 180, 6
         else:

@@ -411,3 +411,39 @@ def test_packed_db_roundtrip(tmp_path):
     np.random.seed(123456)
     got = knn.match_clips(aq[None], tq[None])[0]
     assert np.array_equal(got, fx["knn_pred"])
+
+
+@pytest.mark.parametrize("W,D1,D2,Q", [(3000, 256, 128, 7), (13312, 1024, 384, 8), (77, 128, 128, 1), (20000, 512, 256, 5)])
+def test_fused_two_block_scan_equals_separate_scans(W, D1, D2, Q):
+    """qpg_cand_cosine2_minbycode (audio|text in one pass) == two separate scans, bit for bit."""
+    torch = _torch()
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import PackedRows, new_table, table_to_numpy
+
+    rng = np.random.default_rng(W + D1)
+    a = rng.standard_normal((W, D1)).astype(np.float32)
+    t = rng.standard_normal((W, D2)).astype(np.float32)
+    qa = rng.standard_normal((Q, D1)).astype(np.float32)
+    qt = rng.standard_normal((Q, D2)).astype(np.float32)
+    labels = rng.integers(0, 200, size=W)
+    a[W // 3] = a[2]
+    t[W // 3] = t[2]
+    labels[W // 3] = labels[2]
+    ta, _ = _scan_cosine(a, labels, qa, team=1)
+    tt, _ = _scan_cosine(t, labels, qt, team=1)
+    lib = _lib.load()
+    dev = torch.device("cuda")
+    pa = PackedRows.from_rows(torch.from_numpy(a).to(dev))
+    pt = PackedRows.from_rows(torch.from_numpy(t).to(dev))
+    pf = PackedRows.from_rows(torch.from_numpy(np.concatenate((a, t), axis=1)).to(dev))
+    qf = torch.from_numpy(np.concatenate((qa, qt), axis=1)).to(dev)
+    lab = torch.from_numpy(labels.astype(np.int32)).to(dev)
+    t1, t2 = new_table(Q, dev), new_table(Q, dev)
+    sp = _lib.stream_ptr()
+    for tb in (t1, t2):
+        _lib.check(lib.qpg_table_init(_lib.ptr(tb), Q * 512, sp), "init")
+    _lib.check(lib.qpg_cand_cosine2_minbycode(_lib.ptr(pf.packed), _lib.ptr(pa.sqnorm), _lib.ptr(pt.sqnorm), _lib.ptr(lab),
+                                              W, D1, D2, 0, _lib.ptr(qf), Q, _lib.ptr(t1), _lib.ptr(t2), sp), "fused")
+    g1, g2 = table_to_numpy(t1), table_to_numpy(t2)
+    assert np.array_equal(g1["id"], ta["id"]) and np.array_equal(g1["d"], ta["d"])
+    assert np.array_equal(g2["id"], tt["id"]) and np.array_equal(g2["d"], tt["d"])
