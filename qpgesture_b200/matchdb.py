@@ -197,7 +197,6 @@ class MatchDatabase:
                     self.W * 4 * (aud_dev.shape[1] + txt_dev.shape[1]) <= (8 << 30):
                 self.fused = PackedRows.from_rows(torch.cat((aud_dev, txt_dev), dim=1))
             del aud_dev
-        del txt_dev
             self.aud_k = [m * 6 for m in range(WINDOWS_PER_SEQ)]                    # k = 0,6,...,150
             self.n_db_frm, self.step_sz = 180, 6
         else:
@@ -207,6 +206,7 @@ class MatchDatabase:
             assert len(ks) == WINDOWS_PER_SEQ and ms == list(range(WINDOWS_PER_SEQ))
             self.aud_k = ks
             self.n_db_frm, self.step_sz = WAVVQ_FRAMES, WAVVQ_FRAMES / num_frames_code
+        del txt_dev
         self.txt_k = [m * 8 for m in range(WINDOWS_PER_SEQ)]                        # k = 0,8,...,200
         self.aud_frame = torch.tensor([phase_frame(k) for k in self.aud_k], dtype=torch.int32, device=dev)
         self.txt_frame = torch.tensor([phase_frame(k) for k in self.txt_k], dtype=torch.int32, device=dev)
