@@ -407,18 +407,35 @@ def main():
     ms_e2e, _, _ = timed(step_e2e, args.steps, max(args.warmup, 3))
     assert int(status.max().cpu()) == 0, "tail reported a start-code without window"
 
-    # ---- dominant kernel alone: one audio pass (one launch) at the library's queries-per-pass
+    # ---- dominant kernel alone: ONE pass (one launch) of the scan kernel the step actually uses
     qpp_used = 4 if 6 * args.wavlm_dim > 2048 else 8
-    qa_small = plan.qa[:qpp_used].contiguous()
-    tab_small = new_table(qpp_used, dev)
-    t = db.aud
     sp = _lib.stream_ptr()
+    if plan.fused:
+        qpp_used = 4
+        kernel_name = "cand_cosine2_kernel<QT=4,NCW=12> (audio|text fused pass)"
+        qf_small = plan.qf[:qpp_used].contiguous()
+        t1_small, t2_small = new_table(qpp_used, dev), new_table(qpp_used, dev)
+        alg_bytes = db.W * (4 * (db.aud.D + db.txt.D) + 4)
 
-    def one_pass():
-        _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W, t.D,
-                                                 db.id_offset, _lib.ptr(qa_small), qpp_used, _lib.ptr(tab_small),
-                                                 qpp_used, sp), "cosine")
-    _lib.check(lib.qpg_table_init(_lib.ptr(tab_small), qpp_used * 512, sp), "init")
+        def one_pass():
+            _lib.check(lib.qpg_cand_cosine2_minbycode(_lib.ptr(db.fused.packed), _lib.ptr(db.aud.sqnorm),
+                                                      _lib.ptr(db.txt.sqnorm), _lib.ptr(db.labels), db.W, db.aud.D,
+                                                      db.txt.D, db.id_offset, _lib.ptr(qf_small), qpp_used,
+                                                      _lib.ptr(t1_small), _lib.ptr(t2_small), sp), "cosine2")
+        _lib.check(lib.qpg_table_init(_lib.ptr(t1_small), qpp_used * 512, sp), "init")
+        _lib.check(lib.qpg_table_init(_lib.ptr(t2_small), qpp_used * 512, sp), "init")
+    else:
+        kernel_name = f"cand_cosine_kernel<QT={qpp_used}> (audio pass)"
+        qa_small = plan.qa[:qpp_used].contiguous()
+        tab_small = new_table(qpp_used, dev)
+        t = db.aud
+        alg_bytes = db.algorithmic_bytes("audio")
+
+        def one_pass():
+            _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W,
+                                                     t.D, db.id_offset, _lib.ptr(qa_small), qpp_used,
+                                                     _lib.ptr(tab_small), qpp_used, sp), "cosine")
+        _lib.check(lib.qpg_table_init(_lib.ptr(tab_small), qpp_used * 512, sp), "init")
     for _ in range(5):
         one_pass()
     torch.cuda.synchronize()
@@ -439,12 +456,12 @@ def main():
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = db.algorithmic_bytes("audio")
         traffic = None                                       # dram read+write per launch from the ncu --set full capture
         try:
             tr = json.load(open(os.path.join(ROOT, "profiles", "r01_cosine_traffic.json")))
-            if tr["W"] == db.W and tr["D"] == db.aud.D:
-                traffic = tr["dram_bytes_per_launch"]
+            key = "fused" if plan.fused else "audio"
+            if tr[key]["W"] == db.W and tr[key]["D"] == (db.aud.D + db.txt.D if plan.fused else db.aud.D):
+                traffic = tr[key]["dram_bytes_per_launch"]
         except Exception:
             pass
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
@@ -466,7 +483,7 @@ def main():
                      h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4 + sc_h.numel() * 4 + sp_h.numel() * 4) * world,
                      d2h_bytes_per_step=int(codes_h.numel() * 8) * world),
             gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel=f"cand_cosine_kernel<QT={qpp_used}>", achieved=achieved, peak=peak,
+            roofline=dict(bound="hbm", kernel=kernel_name, achieved=achieved, peak=peak,
                           unit="GB/s", frac=achieved / peak, traffic=traffic, launch_ms=pass_ms,
                           algorithmic_bytes=int(alg_bytes),
                           peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"),
