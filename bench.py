@@ -59,7 +59,7 @@ def parse():
     p.add_argument("--no-vqvae", action="store_true", help="skip the informational VQ-VAE block")
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     p.add_argument("--no-fused", action="store_true", help="separate audio and text scans instead of the fused pass")
-    p.add_argument("--no-overlap", action="store_true", help="do not overlap the sequential tail with the scans")
+    p.add_argument("--overlap", action="store_true", help="overlap the sequential tail with the scans (side stream)")
     return p.parse_args()
 
 
@@ -346,12 +346,12 @@ def main():
     use_graph = not args.no_graph
     try:
         plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph,
-                             overlap_tail=not args.no_overlap, fused_scan=not args.no_fused)
+                             overlap_tail=args.overlap, fused_scan=not args.no_fused)
     except Exception as e:                                   # e.g. NCCL capture unsupported: plain launches
         if rank == 0:
             print(f"[bench] graph capture failed ({type(e).__name__}: {e}); using plain launches", file=sys.stderr)
         use_graph = False
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=not args.no_overlap, fused_scan=not args.no_fused)
+        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=args.overlap, fused_scan=not args.no_fused)
     knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, (my_clips.start, my_clips.stop))] = plan
     plan.qa.copy_(aq_h)
     plan.qt.copy_(tq_h)
