@@ -118,6 +118,10 @@ int qpg_cand_lev_minbycode(const uint32_t* tokens, const int32_t* labels, int64_
 int qpg_lev_distance(const uint32_t* a_tokens, const uint32_t* b_tokens, int64_t n, int32_t* out,
                      void* stream);
 
+/* Prefetch a device buffer into L2 (one prefetch.global.L2 per 128-byte line).  The matcher uses it on the
+ * small tables of the sequential tail (pos_rank, phase_amp, code), which the streaming scans evict. */
+int qpg_l2_prefetch(const void* ptr, size_t bytes, void* stream);
+
 /* ---------------- merge of per-shard tables (multi-GPU / multi-part) -----
  * out[e] = lexicographic min over p < n_parts of parts[p][e].  Used after the
  * all-gather of per-rank tables when database rows are sharded across GPUs.

@@ -419,6 +419,11 @@ class CodeKNN(object):
         Qt = q1 - q0
         _lib.check(lib.qpg_rank512(_lib.ptr(ta_s), Qt, _lib.ptr(p.ra), sp), "qpg_rank512")
         _lib.check(lib.qpg_rank512(_lib.ptr(tt_s), Qt, _lib.ptr(p.rt), sp), "qpg_rank512")
+        # the scans streamed the whole table through L2: re-warm what the tail reads with dependent loads
+        for t_ in (db.pos_rank, db.code, db.phase_amp):
+            nbytes = t_.numel() * t_.element_size()
+            if nbytes <= (32 << 20):
+                _lib.check(lib.qpg_l2_prefetch(_lib.ptr(t_), nbytes, sp), "qpg_l2_prefetch")
         sc, sph = p.seed_code[p.tail], p.seed_phase[p.tail]
         _lib.check(lib.qpg_match_tail(_lib.ptr(ta_s), _lib.ptr(tt_s), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank),
                                       _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),

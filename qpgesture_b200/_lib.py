@@ -54,6 +54,7 @@ SIGNATURES = {
     "qpg_cand_cosine2_minbycode": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _I64, _P, _INT, _P, _P, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
+    "qpg_l2_prefetch": (_INT, [_P, C.c_size_t, _P]),
     "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),
     "qpg_rank512": (_INT, [_P, _INT, _P, _P]),
     "qpg_match_tail": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),

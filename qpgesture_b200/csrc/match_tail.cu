@@ -42,6 +42,14 @@ __global__ void __launch_bounds__(KB) rank512_kernel(const Pair* __restrict__ ta
   ranks[(size_t)q * KB + c] = r;
 }
 
+// pull a buffer into L2 (prefetch.global.L2 per 128-byte line): the streaming scans evict the small tables the
+// sequential tail reads with dependent loads, so they are re-warmed right before it
+__global__ void l2_prefetch_kernel(const char* __restrict__ p, size_t bytes) {
+  const size_t lines = (bytes + 127) / 128;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < lines; i += (size_t)gridDim.x * blockDim.x)
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p + i * 128));
+}
+
 struct ArgMin {
   double v;
   int i;
@@ -66,7 +74,24 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
-__global__ void __launch_bounds__(KB)
+// Two warps per clip: warp 0 follows the audio table, warp 1 the text table.  Lane l owns codes
+// 16*l .. 16*l+15 in registers, so both 512-way arg-mins are register scans + 5 shuffle steps; the two
+// warps exchange (phase distance, 4 codes, next phase) through shared memory at two 64-thread barriers
+// per step.  Ranks and window ids of step s+1 do not depend on the state and are prefetched during step s.
+constexpr int EPL = KB / 32;  // entries per lane
+
+__device__ __forceinline__ void load16(const int32_t* __restrict__ p, int (&v)[EPL]) {
+  const int4* q = reinterpret_cast<const int4*>(p);
+#pragma unroll
+  for (int k = 0; k < EPL / 4; ++k) {
+    const int4 t = q[k];
+    v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+  }
+}
+
+__device__ __forceinline__ void bar64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
+
+__global__ void __launch_bounds__(64)
     match_tail_kernel(const Pair* __restrict__ aud_table, const Pair* __restrict__ txt_table,
                       const int32_t* __restrict__ aud_rank, const int32_t* __restrict__ txt_rank,
                       const int32_t* __restrict__ pos_rank, const int32_t* __restrict__ freq_rank,
@@ -77,146 +102,161 @@ __global__ void __launch_bounds__(KB)
                       int64_t* __restrict__ codes_out, int32_t* __restrict__ vote_out,
                       float* __restrict__ phase_out, int32_t* __restrict__ status_out) {
   __shared__ float prev[8 * PC];
-  __shared__ ArgMin red_a[KB / 32], red_t[KB / 32];
-  __shared__ int s_choice[2];
   __shared__ double s_dist[2];
-  __shared__ long long s_win[2];
-  __shared__ int s_frame[2];
   __shared__ int s_code[2][4];
-  __shared__ float s_tail[2][8 * PC];
-  __shared__ int s_fail;
+  __shared__ int s_bad[2];
 
-  const int b = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
-  // chained launches (one per segment) hand (last code, previous phase) over through `state`
+  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;   // warp 0: audio, 1: text
+  const Pair* table = warp == 0 ? aud_table : txt_table;
+  const int32_t* rank = warp == 0 ? aud_rank : txt_rank;
+  const int32_t* frame = warp == 0 ? aud_frame : txt_frame;
+
   float* st_b = state ? state + (size_t)b * (8 * PC + 4) : nullptr;
   const bool resume = seg_begin > 0 && st_b != nullptr;
-  if (c < 8 * PC) prev[c] = resume ? st_b[4 + c] : seed_phase[(size_t)b * 8 * PC + c];
-  if (c == 0) s_fail = 0;
+  for (int e = threadIdx.x; e < 8 * PC; e += 64) prev[e] = resume ? st_b[4 + e] : seed_phase[(size_t)b * 8 * PC + e];
   int last = resume ? __float_as_int(st_b[0]) : seed_code[b];
   if (resume && __float_as_int(st_b[1]) != 0) {   // an earlier segment already failed
-    if (c == 0) status_out[b] = 1;
+    if (threadIdx.x == 0) status_out[b] = 1;
     return;
   }
-  const double freq_term = __dmul_rn((double)freq_rank[c], 0.05);
+  double freq_term[EPL];
+  {
+    int fr[EPL];
+    load16(freq_rank + lane * EPL, fr);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) freq_term[k] = __dmul_rn((double)fr[k], 0.05);
+  }
   const int n_steps = (seg_begin + seg_count) * 8;
   const int first_step = seg_begin * 8;
   const size_t q0 = (size_t)b * n_seg * 8;
-  // ranks and window ids of a step do not depend on the sequential state: keep one step in flight
-  int ra_n = aud_rank[(q0 + first_step) * KB + c], rt_n = txt_rank[(q0 + first_step) * KB + c];
-  long long ida_n = (long long)aud_table[(q0 + first_step) * KB + c].id;
-  long long idt_n = (long long)txt_table[(q0 + first_step) * KB + c].id;
+
+  int rk_n[EPL];
+  long long id_n[EPL];
+  {
+    const size_t base = (q0 + first_step) * KB + lane * EPL;
+    load16(rank + base, rk_n);
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) id_n[k] = (long long)table[base + k].id;
+  }
   __syncthreads();
 
   int code29 = last;
   for (int st = first_step; st < n_steps; ++st) {
     const int g = st >> 3, s = st & 7;
     const size_t q = q0 + st;
-    const int ra = ra_n, rt = rt_n;
-    const long long ida = ida_n, idt = idt_n;
-    // pos_score + freq_score*0.05, then + rank (same IEEE operations as NumPy, GestureKNN.py:545,554,575)
-    const int pr = pos_rank[(size_t)last * KB + c];
-    if (st + 1 < n_steps) {
-      ra_n = aud_rank[(q + 1) * KB + c];
-      rt_n = txt_rank[(q + 1) * KB + c];
-      ida_n = (long long)aud_table[(q + 1) * KB + c].id;
-      idt_n = (long long)txt_table[(q + 1) * KB + c].id;
+    int pr[EPL], rk[EPL];
+    long long id[EPL];
+    load16(pos_rank + (size_t)last * KB + lane * EPL, pr);           // depends on the state: round trip 1
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      rk[k] = rk_n[k];
+      id[k] = id_n[k];
     }
-    const double base = __dadd_rn((double)pr, freq_term);
-    ArgMin a{__dadd_rn(base, (double)ra), c};
-    ArgMin t{__dadd_rn(base, (double)rt), c};
-    a = warp_argmin(a);
-    t = warp_argmin(t);
-    if (lane == 0) {
-      red_a[warp] = a;
-      red_t[warp] = t;
+    if (st + 1 < n_steps) {                                           // state independent: overlaps this step
+      const size_t base = (q + 1) * KB + lane * EPL;
+      load16(rank + base, rk_n);
+#pragma unroll
+      for (int k = 0; k < EPL; ++k) id_n[k] = (long long)table[base + k].id;
     }
-    __syncthreads();
+    // combined = (pos_score + freq_score*0.05) + rank, same IEEE operations as NumPy (GestureKNN.py:545,554,575)
+    ArgMin best{1e300, KB};
+    long long best_id = -1;
+#pragma unroll
+    for (int k = 0; k < EPL; ++k) {
+      const double v = __dadd_rn(__dadd_rn((double)pr[k], freq_term[k]), (double)rk[k]);
+      if (v < best.v) {            // ascending k: the first minimum of this lane wins
+        best.v = v;
+        best.i = lane * EPL + k;
+        best_id = id[k];
+      }
+    }
     {
-      // every warp reduces the 16 partials redundantly: no second hand-off through shared memory
-      ArgMin x = lane < KB / 32 ? red_a[lane] : ArgMin{1e300, KB};
-      ArgMin y = lane < KB / 32 ? red_t[lane] : ArgMin{1e300, KB};
-      x = warp_argmin(x);
-      y = warp_argmin(y);
-      if (c == x.i) s_win[0] = ida;
-      if (c == y.i) s_win[1] = idt;
-    }
-    __syncthreads();
-    // warps 0 / 1 score the audio / text candidate by phase continuity (GestureKNN.py:627-644)
-    if (warp < 2) {
-      const long long w = s_win[warp];
-      if (w < 0 || w >= n_seq * WIN) {
-        if (lane == 0) s_fail = 1;
-      } else {
-        const long long j = w / WIN;
-        const int m = (int)(w - j * WIN);
-        const int f = (warp == 0 ? aud_frame : txt_frame)[m];
-        const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;  // rows f .. f+7
-        if (lane < 4) s_code[warp][lane] = code[(size_t)j * NCODE + m + lane];
-        float tl[4];
+      // lexicographic (value, code) arg-min across lanes; carry the window id along
 #pragma unroll
-        for (int k = 0; k < 4; ++k) tl[k] = head[24 * PC + lane + 32 * k];   // window frames 24..31 (next prev)
-        double av[4], bv[4], sa = 0.0, sb = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int e2 = lane + 32 * k, row = e2 >> 4, col = e2 & 15;
-          const float fa = row < 5 ? prev[(3 + row) * PC + col] : head[(row - 5) * PC + col];
-          const float fb = row < 3 ? prev[(5 + row) * PC + col] : head[(row - 3) * PC + col];
-          av[k] = (double)fa;
-          bv[k] = (double)fb;
-          sa = fma(av[k], av[k], sa);
-          sb = fma(bv[k], bv[k], sb);
-        }
-        sa = warp_sum(sa);
-        sb = warp_sum(sb);
-        const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
-        double acc = 0.0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const double d = av[k] / na - bv[k] / nb;
-          acc = fma(d, d, acc);
-        }
-        acc = 0.5 * warp_sum(acc);
-#pragma unroll
-        for (int k = 0; k < 4; ++k) s_tail[warp][lane + 32 * k] = tl[k];
-        if (lane == 0) {
-          s_dist[warp] = acc;
-          s_frame[warp] = f;
+      for (int o = 16; o >= 1; o >>= 1) {
+        const double ov = __shfl_xor_sync(0xffffffffu, best.v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, best.i, o);
+        const long long oid = __shfl_xor_sync(0xffffffffu, best_id, o);
+        if (ov < best.v || (ov == best.v && oi < best.i)) {
+          best.v = ov;
+          best.i = oi;
+          best_id = oid;
         }
       }
     }
-    __syncthreads();
-    if (s_fail) {
-      if (c == 0) {
+    // phase continuity of this warp's candidate (GestureKNN.py:627-644): round trip 2
+    const long long w = best_id;
+    const bool bad = w < 0 || w >= n_seq * WIN;
+    float tl[4] = {0.f, 0.f, 0.f, 0.f};
+    double dist = 0.0;
+    if (!bad) {
+      const long long j = w / WIN;
+      const int m = (int)(w - j * WIN);
+      const int f = frame[m];
+      const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;   // rows f .. f+7 ; rows f+24 .. f+31 = next prev
+      int my_code = 0;
+      if (lane < 4) my_code = code[(size_t)j * NCODE + m + lane];
+      double av[4], bv[4], sa = 0.0, sb = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int e2 = lane + 32 * k, row = e2 >> 4, col = e2 & 15;
+        const float fa = row < 5 ? prev[(3 + row) * PC + col] : head[(row - 5) * PC + col];
+        const float fb = row < 3 ? prev[(5 + row) * PC + col] : head[(row - 3) * PC + col];
+        tl[k] = head[24 * PC + e2];
+        av[k] = (double)fa;
+        bv[k] = (double)fb;
+        sa = fma(av[k], av[k], sa);
+        sb = fma(bv[k], bv[k], sb);
+      }
+      sa = warp_sum(sa);
+      sb = warp_sum(sb);
+      const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
+      double acc = 0.0;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const double d = av[k] / na - bv[k] / nb;
+        acc = fma(d, d, acc);
+      }
+      dist = 0.5 * warp_sum(acc);
+      if (lane < 4) s_code[warp][lane] = my_code;
+    }
+    if (lane == 0) {
+      s_dist[warp] = dist;
+      s_bad[warp] = bad ? 1 : 0;
+    }
+    bar64(1);                                                         // both candidates scored
+    if (s_bad[0] | s_bad[1]) {
+      if (threadIdx.x == 0) {
         status_out[b] = 1;
         if (st_b) st_b[1] = __int_as_float(1);
       }
       return;
     }
-    const int final_idx = (s_dist[0] <= s_dist[1]) ? 0 : 1;  // tmp_distance.index(min(...)): audio wins ties
-    float new_prev = 0.f;
-    if (c < 8 * PC) new_prev = s_tail[final_idx][c];
+    const int final_idx = (s_dist[0] <= s_dist[1]) ? 0 : 1;           // tmp_distance.index(min(...)): audio wins ties
     const int p1 = s_code[final_idx][1], p3 = s_code[final_idx][3];
-    if (c < 4) {
-      const int p = s * 4 + c;
-      if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = s_code[final_idx][c];
+    if (warp == final_idx) {                                          // the winner installs the next phase
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        prev[lane + 32 * k] = tl[k];
+        if (phase_out) phase_out[(q * 8) * PC + lane + 32 * k] = tl[k];
+      }
+      if (lane < 4) {
+        const int p = s * 4 + lane;
+        if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = s_code[final_idx][lane];
+      }
+      if (lane == 0) vote_out[q] = final_idx;
     }
-    if (c == 0) vote_out[q] = final_idx;
-    if (s == 7) code29 = p1;  // produced code #30 seeds the next segment (GestureKNN.py:800)
+    if (s == 7) code29 = p1;   // produced code #30 seeds the next segment (GestureKNN.py:800)
     last = (s == 7) ? code29 : p3;
-    __syncthreads();  // everyone has read prev / s_* of this step
-    if (c < 8 * PC) {
-      prev[c] = new_prev;
-      if (phase_out) phase_out[(q * 8) * PC + c] = new_prev;
-    }
-    __syncthreads();
+    bar64(2);                                                         // prev / s_* may be overwritten
   }
-  if (c == 0) status_out[b] = 0;
+  if (threadIdx.x == 0) status_out[b] = 0;
   if (st_b) {
-    if (c == 0) {
+    if (threadIdx.x == 0) {
       st_b[0] = __int_as_float(last);
       st_b[1] = __int_as_float(0);
     }
-    if (c < 8 * PC) st_b[4 + c] = prev[c];
+    for (int e = threadIdx.x; e < 8 * PC; e += 64) st_b[4 + e] = prev[e];
   }
 }
 
@@ -224,6 +264,17 @@ __global__ void __launch_bounds__(KB)
 }  // namespace qpg
 
 using namespace qpg;
+
+extern "C" int qpg_l2_prefetch(const void* ptr, size_t bytes, void* stream) {
+  if (bytes == 0) return QPG_OK;
+  QPG_CHECK_ARG(ptr != nullptr, "null pointer");
+  const size_t lines = (bytes + 127) / 128;
+  size_t blocks = (lines + 255) / 256;
+  if (blocks > 1184) blocks = 1184;
+  l2_prefetch_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const char*>(ptr), bytes);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
 
 extern "C" int qpg_table_merge(const qpg_pair_t* parts, int n_parts, int64_t n_entries, qpg_pair_t* out,
                                void* stream) {
@@ -258,7 +309,7 @@ static int match_tail_launch(const qpg_pair_t* aud_table, const qpg_pair_t* txt_
   QPG_CHECK_ARG(aud_table && txt_table && aud_rank && txt_rank && pos_rank && freq_rank && code && phase_amp &&
                     aud_frame && txt_frame && seed_code && seed_phase && codes_out && vote_out && status_out,
                 "null pointer");
-  match_tail_kernel<<<n_clips, KB, 0, (cudaStream_t)stream>>>(
+  match_tail_kernel<<<n_clips, 64, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const Pair*>(aud_table), reinterpret_cast<const Pair*>(txt_table), aud_rank, txt_rank,
       pos_rank, freq_rank, code, n_seq, phase_amp, aud_frame, txt_frame, seed_code, seed_phase, n_seg, seg_begin,
       seg_count, state, codes_out, vote_out, phase_out, status_out);
