@@ -447,3 +447,53 @@ def test_fused_two_block_scan_equals_separate_scans(W, D1, D2, Q):
     g1, g2 = table_to_numpy(t1), table_to_numpy(t2)
     assert np.array_equal(g1["id"], ta["id"]) and np.array_equal(g1["d"], ta["d"])
     assert np.array_equal(g2["id"], tt["id"]) and np.array_equal(g2["d"], tt["d"])
+
+
+def test_reference_call_path_predict_code_from_audio(tmp_path):
+    """The reference's own call sequence (main_codebook, GestureKNN.py:816-845): load_db_codebook ->
+    predict_code_from_audio with the shipped literals, on npz files, against the recorded knn_pred."""
+    from qpgesture_b200 import GestureKNN as G
+    from qpgesture_b200 import data_processing as dp
+    from qpgesture_b200 import synth
+
+    fx, train, test, code, sig = load_case(CASES[0])
+    p = synth.write_npz_set(str(tmp_path), train, test, code, sig, object_phase=False)
+    (train_mfcc, train_code, test_mfcc, train_feat, test_feat, train_wavlm, test_wavlm, train_wavlm_feat,
+     test_wavlm_feat, speech_features, test_speech_features, train_speech_features_feat, test_speech_features_feat,
+     train_wavvq_feat, test_wavvq_feat, train_phase, test_phase, train_context, test_context) = dp.load_db_codebook(
+        p.train_database, p.train_codebook, p.test_data, p.train_wavlm, p.test_wavlm, p.train_wavvq, p.test_wavvq)
+    G.seed_everything()
+    pred = G.predict_code_from_audio(
+        train_mfcc, train_code, test_mfcc, {}, train_feat, test_feat, train_wavlm, test_wavlm, train_wavlm_feat,
+        test_wavlm_feat, speech_features, test_speech_features, train_speech_features_feat, test_speech_features_feat,
+        train_wavvq_feat, test_wavvq_feat, train_phase, test_phase, train_context, test_context, use_feature=True,
+        use_wavlm=True, use_freq=False, use_speechfeat=False, use_wavvq=False, use_phase=True, use_txt=True,
+        use_aud=True, frames=0, codebook_signature=p.codebook_signature, train_codebook=p.train_codebook, tail="numpy")
+    # tail="numpy" replays the reference's own argsort calls: identical whenever this machine orders the
+    # frequency-rank ties like the recording machine did
+    from qpgesture_b200.matchdb import freq_rank_from_code
+    if np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
+        assert np.array_equal(pred, fx["knn_pred"])
+    assert pred.shape == fx["knn_pred"].shape and pred.dtype == np.int64
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_golden_mode_b_segment(path):
+    """Mode B (vq-wav2vec Levenshtein) search_code_knn with explicit seeds vs the reference's recorded codes."""
+    from qpgesture_b200 import data_processing as dp
+    from qpgesture_b200.matchdb import freq_rank_from_code
+
+    fx, train, test, code, sig = load_case(path)
+    if fx["codes_b"].shape == (1,):
+        pytest.skip("reference raised IndexError on this case")
+    knn = _knn_from_case("B", train, code, sig, fx, "numpy")
+    clip = dp.stack_wavvq_feat(test["wavvq"])[0]
+    ctx = test["context"].squeeze(2)[0]
+    codes, phases, vote = knn.search_code_knn(clip_test=clip, desired_k=0, use_wavlm=False, use_feature=True,
+                                              use_freq=False, seed_code=int(fx["init_code"]), use_wavvq=True,
+                                              use_phase=True, seed_phase=fx["init_phase"], use_txt=True,
+                                              clip_context=ctx, use_aud=True)
+    assert codes.shape == (30,) and phases.shape == (8, 8, 16) and vote.shape == (8,)
+    # integer Levenshtein ranks are dominated by ties; NumPy's tie order is platform defined
+    if np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
+        assert np.array_equal(codes, fx["codes_b"]) and np.array_equal(vote, fx["vote_b"])
