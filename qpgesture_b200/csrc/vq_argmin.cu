@@ -15,72 +15,70 @@ namespace qpg {
 namespace {
 
 constexpr int TM = 16;        // latents per CTA
-constexpr int THREADS = 128;  // each thread owns K/THREADS codes
+constexpr int THREADS = 128;  // one code per thread; the codebook is split over gridDim.y CTAs
 
-__global__ void sqnorm_rows_kernel(const float* __restrict__ a, int64_t n, int D, float* __restrict__ out) {
-  const int64_t row = blockIdx.x * (int64_t)(blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (row >= n) return;
-  double s = 0.0;
-  for (int d = lane; d < D; d += 32) {
-    const double v = (double)a[row * D + d];
-    s = fma(v, v, s);
-  }
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  if (lane == 0) out[row] = (float)s;
+// order-preserving map float -> uint32 (handles the slightly negative distances rounding can produce)
+__device__ __forceinline__ uint32_t ordered_u32(float f) {
+  const uint32_t u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_f32(uint32_t k) {
+  return __uint_as_float((k & 0x80000000u) ? (k & 0x7fffffffu) : ~k);
 }
 
-template <int CPT>  // codes per thread
+__global__ void vq_key_init_kernel(unsigned long long* __restrict__ keys, int64_t M) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < M) keys[i] = ~0ull;
+}
+
+__global__ void vq_key_finish_kernel(int64_t* __restrict__ idx_io, float* __restrict__ min_out, int64_t M) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= M) return;
+  const unsigned long long key = (unsigned long long)idx_io[i];
+  if (min_out) min_out[i] = unordered_f32((uint32_t)(key >> 32));
+  idx_io[i] = (int64_t)(key & 0xffffffffull);
+}
+
+// keys[m] = min over codes of (ordered(dist) << 32 | k): lexicographic (distance, code index) -> first minimum.
+// The latent tile is converted to float64 once in shared memory, so the inner loop is 1 F2F per 16 DFMA.
 __global__ void __launch_bounds__(THREADS)
     vq_argmin_kernel(const float* __restrict__ x, const float* __restrict__ cb, int64_t M, int D, int K,
-                     int64_t* __restrict__ idx_out, float* __restrict__ min_out) {
+                     unsigned long long* __restrict__ keys) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  float* xs = reinterpret_cast<float*>(smem_raw);             // [TM][D]
-  float* xn = xs + (size_t)TM * D;                            // [TM] squared norms (float32)
-  float* red_v = xn + TM;                                     // [TM][THREADS/32]
-  int* red_i = reinterpret_cast<int*>(red_v + TM * (THREADS / 32));
+  double* xs = reinterpret_cast<double*>(smem_raw);           // [TM][Dp] float64 copies of the latents
+  float* xn = reinterpret_cast<float*>(xs + (size_t)TM * ((D + 3) & ~3));   // [TM] squared norms (float32)
+  const int Dp = (D + 3) & ~3;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int64_t m0 = (int64_t)blockIdx.x * TM;
 
-  for (int i = tid; i < TM * D; i += THREADS) {
-    const int64_t m = m0 + i / D;
-    xs[i] = m < M ? x[m * D + (i % D)] : 0.f;
+  for (int i = tid; i < TM * Dp; i += THREADS) {
+    const int r = i / Dp, d = i - r * Dp;
+    const int64_t m = m0 + r;
+    xs[i] = (m < M && d < D) ? (double)x[m * D + d] : 0.0;
   }
   __syncthreads();
   for (int r = warp; r < TM; r += THREADS / 32) {
     double s = 0.0;
-    for (int d = lane; d < D; d += 32) {
-      const double v = (double)xs[r * D + d];
-      s = fma(v, v, s);
-    }
+    for (int d = lane; d < Dp; d += 32) s = fma(xs[r * Dp + d], xs[r * Dp + d], s);
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) xn[r] = (float)s;
   }
   __syncthreads();
 
-  float best_v[TM];
-  int best_i[TM];
-#pragma unroll
-  for (int r = 0; r < TM; ++r) {
-    best_v[r] = INFINITY;
-    best_i[r] = 0x7fffffff;
-  }
-  // codes k = tid + c*THREADS (ascending in c, so a strict < keeps the first minimum per thread)
-  for (int c = 0; c < CPT; ++c) {
-    const int k = tid + c * THREADS;
-    if (k >= K) break;
+  const int k = blockIdx.y * THREADS + tid;
+  if (k < K) {
     const float* row = cb + (size_t)k * D;
     double acc[TM], kn = 0.0;
 #pragma unroll
     for (int r = 0; r < TM; ++r) acc[r] = 0.0;
-    for (int d = 0; d < D; d += 4) {
+    const bool vec = (D & 3) == 0;
+    for (int d = 0; d < Dp; d += 4) {
       float4 cv;
-      if (d + 3 < D && ((D & 3) == 0)) {
+      if (vec) {
         cv = *reinterpret_cast<const float4*>(row + d);
       } else {
-        cv.x = row[d];
+        cv.x = d < D ? row[d] : 0.f;
         cv.y = d + 1 < D ? row[d + 1] : 0.f;
         cv.z = d + 2 < D ? row[d + 2] : 0.f;
         cv.w = d + 3 < D ? row[d + 3] : 0.f;
@@ -92,59 +90,26 @@ __global__ void __launch_bounds__(THREADS)
       kn = fma(c3, c3, kn);
 #pragma unroll
       for (int r = 0; r < TM; ++r) {
-        const float* xr = xs + r * D + d;
+        const double2 x01 = *reinterpret_cast<const double2*>(xs + (size_t)r * Dp + d);      // broadcast reads
+        const double2 x23 = *reinterpret_cast<const double2*>(xs + (size_t)r * Dp + d + 2);
         double a = acc[r];
-        a = fma((double)xr[0], c0, a);
-        if (d + 1 < D) a = fma((double)xr[1], c1, a);
-        if (d + 2 < D) a = fma((double)xr[2], c2, a);
-        if (d + 3 < D) a = fma((double)xr[3], c3, a);
+        a = fma(x01.x, c0, a);
+        a = fma(x01.y, c1, a);
+        a = fma(x23.x, c2, a);
+        a = fma(x23.y, c3, a);
         acc[r] = a;
       }
     }
     const float knf = (float)kn;
 #pragma unroll
     for (int r = 0; r < TM; ++r) {
-      const float dotf = (float)acc[r];
-      const float dist = __fadd_rn(__fsub_rn(xn[r], __fmul_rn(2.0f, dotf)), knf);
-      if (dist < best_v[r]) {
-        best_v[r] = dist;
-        best_i[r] = k;
+      if (m0 + r < M) {
+        // the reference's float32 formula on a correctly rounded inner product (bottleneck.py:123)
+        const float dist = __fadd_rn(__fsub_rn(xn[r], __fmul_rn(2.0f, (float)acc[r])), knf);
+        const unsigned long long key = ((unsigned long long)ordered_u32(dist) << 32) | (unsigned long long)k;
+        atomicMin(&keys[m0 + r], key);
       }
     }
-  }
-  // block argmin per latent: (value, index) lexicographic -> first minimum overall
-#pragma unroll
-  for (int r = 0; r < TM; ++r) {
-    float v = best_v[r];
-    int i = best_i[r];
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, v, o);
-      const int oi = __shfl_xor_sync(0xffffffffu, i, o);
-      if (ov < v || (ov == v && oi < i)) {
-        v = ov;
-        i = oi;
-      }
-    }
-    if (lane == 0) {
-      red_v[r * (THREADS / 32) + warp] = v;
-      red_i[r * (THREADS / 32) + warp] = i;
-    }
-  }
-  __syncthreads();
-  if (tid < TM && m0 + tid < M) {
-    float v = red_v[tid * (THREADS / 32)];
-    int i = red_i[tid * (THREADS / 32)];
-    for (int w = 1; w < THREADS / 32; ++w) {
-      const float ov = red_v[tid * (THREADS / 32) + w];
-      const int oi = red_i[tid * (THREADS / 32) + w];
-      if (ov < v || (ov == v && oi < i)) {
-        v = ov;
-        i = oi;
-      }
-    }
-    idx_out[m0 + tid] = i;
-    if (min_out) min_out[m0 + tid] = v;
   }
 }
 
@@ -167,20 +132,24 @@ extern "C" int qpg_vq_argmin_f32(const float* x, const float* codebook, int64_t 
   QPG_CHECK_ARG(M >= 0 && D > 0 && K > 0, "M >= 0, D > 0, K > 0");
   if (M == 0) return QPG_OK;
   QPG_CHECK_ARG(x && codebook && idx_out, "null pointer");
-  QPG_CHECK_ARG(K <= 8 * THREADS, "K <= 1024");
   QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(codebook) & 15) == 0, "codebook must be 16-byte aligned");
-  const size_t smem = (size_t)TM * D * 4 + TM * 4 + TM * (THREADS / 32) * 8 + 64;
+  const int Dp = (D + 3) & ~3;
+  const size_t smem = (size_t)TM * Dp * sizeof(double) + TM * sizeof(float) + 64;
   QPG_CHECK_ARG(smem <= 200 * 1024, "D too large");
-  const int64_t blocks = (M + TM - 1) / TM;
-  const int cpt = (K + THREADS - 1) / THREADS;
   cudaStream_t st = (cudaStream_t)stream;
-  if (cpt <= 4) {
-    QPG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_argmin_kernel<4><<<(unsigned)blocks, THREADS, smem, st>>>(x, codebook, M, D, K, idx_out, min_out);
-  } else {
-    QPG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vq_argmin_kernel<8><<<(unsigned)blocks, THREADS, smem, st>>>(x, codebook, M, D, K, idx_out, min_out);
+  // idx_out doubles as the 64-bit key buffer (ordered distance << 32 | code) until the finish kernel
+  unsigned long long* keys = reinterpret_cast<unsigned long long*>(idx_out);
+  vq_key_init_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(keys, M);
+  QPG_LAUNCH_CHECK();
+  static bool attr_set = false;
+  if (!attr_set) {
+    QPG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
   }
+  dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((K + THREADS - 1) / THREADS));
+  vq_argmin_kernel<<<grid, THREADS, smem, st>>>(x, codebook, M, D, K, keys);
+  QPG_LAUNCH_CHECK();
+  vq_key_finish_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(idx_out, min_out, M);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

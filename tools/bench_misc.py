@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Timings of the smaller kernels of the hot path (one JSON line each): Levenshtein min-by-code scan (K10),
+VQ L2-argmin (K1), rank512, table merge."""
+import json, os, sys
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from qpgesture_b200 import _lib
+from qpgesture_b200.matchdb import new_table
+
+def timed(fn, reps=20):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / reps
+
+def main():
+    lib = _lib.load(); dev = torch.device("cuda"); sp = _lib.stream_ptr()
+    g = torch.Generator(device=dev); g.manual_seed(0)
+    for W, Q in ((13312, 48), (1_000_000, 48)):
+        tok = torch.randint(0, 102400, (W, 12), device=dev, dtype=torch.int32, generator=g)
+        qt = torch.randint(0, 102400, (Q, 12), device=dev, dtype=torch.int32, generator=g)
+        lab = torch.randint(0, 512, (W,), device=dev, dtype=torch.int32, generator=g)
+        tab = new_table(Q, dev)
+        lib.qpg_table_init(_lib.ptr(tab), Q * 512, sp)
+        ms = timed(lambda: lib.qpg_cand_lev_minbycode(_lib.ptr(tok), _lib.ptr(lab), W, 0, _lib.ptr(qt), Q, _lib.ptr(tab), sp))
+        print(json.dumps(dict(kernel="cand_lev_kernel", W=W, Q=Q, ms=ms, pairs_per_s=W * Q / ms * 1e3,
+                              dp_cells_per_s=W * Q * 121 / ms * 1e3, bytes_per_s=W * 52 * (-(-Q // 4)) / ms * 1e3)), flush=True)
+    cb = torch.randn((512, 512), device=dev, generator=g)
+    for M in (30, 960, 65536):
+        x = torch.randn((M, 512), device=dev, generator=g)
+        idx = torch.empty(M, dtype=torch.int64, device=dev); mind = torch.empty(M, device=dev)
+        ms = timed(lambda: lib.qpg_vq_argmin_f32(_lib.ptr(x), _lib.ptr(cb), M, 512, 512, _lib.ptr(idx), _lib.ptr(mind), sp),
+                   reps=20 if M < 10000 else 3)
+        print(json.dumps(dict(kernel="vq_argmin_kernel", M=M, ms=ms, latents_per_s=M / ms * 1e3,
+                              tflops=2 * M * 512 * 512 / ms / 1e9)), flush=True)
+    Q = 48
+    tab = new_table(Q, dev); lib.qpg_table_init(_lib.ptr(tab), Q * 512, sp)
+    ranks = torch.empty((Q, 512), dtype=torch.int32, device=dev)
+    print(json.dumps(dict(kernel="rank512_kernel", Q=Q, ms=timed(lambda: lib.qpg_rank512(_lib.ptr(tab), Q, _lib.ptr(ranks), sp)))))
+    parts = torch.zeros((8, Q, 512, 2), dtype=torch.int64, device=dev); out = new_table(Q, dev)
+    print(json.dumps(dict(kernel="table_merge_kernel", parts=8, Q=Q,
+                          ms=timed(lambda: lib.qpg_table_merge(_lib.ptr(parts), 8, Q * 512, _lib.ptr(out), sp)))))
+
+if __name__ == "__main__":
+    main()
