@@ -158,9 +158,10 @@ class CodeKNN(object):
         self.c2s = {i: self.db.signature[i] for i in range(codebook_size)}       # GestureKNN.py:475-479
 
     def code_to_freq(self):
+        """GestureKNN.py:481-499; the rank transform of it (:544) lives in self.db.freq_rank."""
         from .matchdb import code_to_freq
-        self.freq_dist_cands = None                                             # rank table lives in self.db
-        self.c2f = None
+        self.freq_dist_cands = list(code_to_freq(self.code_train))
+        self.c2f = dict(enumerate(self.freq_dist_cands))
 
     def init_code_phase(self):
         """GestureKNN.py:462-473: two draws from NumPy's global legacy RNG."""

@@ -16,7 +16,7 @@ bottleneck.py:39-94) is out of scope and raises.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import numpy as np
 import torch
