@@ -72,6 +72,14 @@ size_t qpg_packed_bytes(int64_t W, int D);
 int qpg_pack_rows_f32(const float* rows, int64_t W, int D, float* packed, double* row_sqnorm,
                       void* stream);
 
+/* ---------------- device-side feature stacking (database / query build) -------------------------
+ * out[(n*n_rows + r)*6C + i*C + c] = interp[n, row_step*r + 2i, c], i < 6 (zero past T_out), where
+ * interp = F.interpolate(wavlm^T, size=T_out, mode='linear', align_corners=True)^T reproduced bit for
+ * bit (data_processing.py:255-274).  Database windows: n_rows = 26, row_step = T_out/30 (GestureKNN.py:
+ * 671-690); query steps: n_rows = 8, row_step = 4*T_out/30 (:528,:565).  wavlm [n_seq, T_in, C] f32. */
+int qpg_stack_wavlm_rows(const float* wavlm, int64_t n_seq, int T_in, int C, int T_out, int n_rows, int row_step,
+                         float* out, void* stream);
+
 /* ---------------- candidate distance, cosine, fused min-by-start-code ----
  * For each of Q query vectors q[Q, D] (float32) and every window w < W:
  *   dist = 0.5*|| q/|q| - x_w/|x_w| ||^2      (sklearn paired cosine distance,

@@ -48,6 +48,7 @@ SIGNATURES = {
     "qpg_tune_cosine_alternate": (_INT, [_INT]),
     "qpg_packed_bytes": (C.c_size_t, [_I64, _INT]),
     "qpg_pack_rows_f32": (_INT, [_P, _I64, _INT, _P, _P, _P]),
+    "qpg_stack_wavlm_rows": (_INT, [_P, _I64, _INT, _INT, _INT, _INT, _INT, _P, _P]),
     "qpg_table_init": (_INT, [_P, _I64, _P]),
     "qpg_cand_cosine_minbycode": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _P]),
     "qpg_cand_cosine_minbycode_team": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _INT, _P]),

@@ -154,3 +154,24 @@ def load_match_inputs(data_file, codepath, test_data_path, train_wavlm, test_wav
         out["aud_q"] = wavvq_tokens(vq_te[:, [int(i) for i in i_list], :])   # [M, 8, 11]
         out["txt_q"] = np.ascontiguousarray(t_ctx[:, [int(i / 398 * 30) for i in i_list], :], dtype=np.float32)
     return out
+
+
+def wavlm_rows_on_device(wavlm, kind: str = "window", device=None):
+    """Device-side replacement of interpolate_wavlm + wavlm_window_rows / wavlm_query_rows (row 8(f).1):
+    raw WavLM frames [n, 199, C] -> float32 CUDA tensor [n*26, 6C] (kind='window') or [n, 8, 6C] (kind='query'),
+    bit-identical to the host path (qpg_stack_wavlm_rows)."""
+    from . import _lib
+
+    lib = _lib.load()
+    dev = torch.device(device if device is not None else "cuda")
+    w = torch.as_tensor(np.ascontiguousarray(wavlm, dtype=np.float32) if isinstance(wavlm, np.ndarray) else wavlm)
+    w = w.to(device=dev, dtype=torch.float32).contiguous()
+    n, t_in, c = w.shape
+    t_out = t_in // num_frames_code * num_frames_code
+    step = t_out // num_frames_code
+    n_rows, row_step = (WINDOWS_PER_SEQ, step) if kind == "window" else (t_out // (STEP_SZ * step), STEP_SZ * step)
+    out = torch.empty((n * n_rows, NUM_AUDIO_FEAT_FRAMES * c), dtype=torch.float32, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(lib.qpg_stack_wavlm_rows(_lib.ptr(w), n, t_in, c, t_out, n_rows, row_step, _lib.ptr(out),
+                                            _lib.stream_ptr()), "qpg_stack_wavlm_rows")
+    return out if kind == "window" else out.view(n, n_rows, -1)

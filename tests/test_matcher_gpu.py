@@ -497,3 +497,17 @@ def test_golden_mode_b_segment(path):
     # integer Levenshtein ranks are dominated by ties; NumPy's tie order is platform defined
     if np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
         assert np.array_equal(codes, fx["codes_b"]) and np.array_equal(vote, fx["vote_b"])
+
+
+def test_device_feature_stacking_bit_exact():
+    """Row 8(f).1: qpg_stack_wavlm_rows == torch F.interpolate + tap stacking + row selection, bit for bit."""
+    from qpgesture_b200 import data_processing as dp
+
+    rng = np.random.default_rng(4)
+    for n, C in ((5, 32), (3, 1024)):
+        wav = rng.standard_normal((n, 199, C)).astype(np.float32)
+        interp = dp.interpolate_wavlm(wav)
+        got_w = dp.wavlm_rows_on_device(wav, "window").cpu().numpy()
+        got_q = dp.wavlm_rows_on_device(wav, "query").cpu().numpy()
+        assert np.array_equal(got_w, dp.wavlm_window_rows(interp))
+        assert np.array_equal(got_q, dp.wavlm_query_rows(interp))
