@@ -169,7 +169,7 @@ def wavlm_rows_on_device(wavlm, kind: str = "window", device=None):
     n, t_in, c = w.shape
     t_out = t_in // num_frames_code * num_frames_code
     step = t_out // num_frames_code
-    n_rows, row_step = (WINDOWS_PER_SEQ, step) if kind == "window" else (t_out // (STEP_SZ * step), STEP_SZ * step)
+    n_rows, row_step = (WINDOWS_PER_SEQ, step) if kind == "window" else (-(-t_out // (STEP_SZ * step)), STEP_SZ * step)
     out = torch.empty((n * n_rows, NUM_AUDIO_FEAT_FRAMES * c), dtype=torch.float32, device=dev)
     with torch.cuda.device(dev):
         _lib.check(lib.qpg_stack_wavlm_rows(_lib.ptr(w), n, t_in, c, t_out, n_rows, row_step, _lib.ptr(out),

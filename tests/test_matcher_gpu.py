@@ -509,5 +509,7 @@ def test_device_feature_stacking_bit_exact():
         interp = dp.interpolate_wavlm(wav)
         got_w = dp.wavlm_rows_on_device(wav, "window").cpu().numpy()
         got_q = dp.wavlm_rows_on_device(wav, "query").cpu().numpy()
-        assert np.array_equal(got_w, dp.wavlm_window_rows(interp))
-        assert np.array_equal(got_q, dp.wavlm_query_rows(interp))
+        want_w, want_q = dp.wavlm_window_rows(interp), dp.wavlm_query_rows(interp)
+        assert got_w.shape == want_w.shape and got_q.shape == want_q.shape, (got_w.shape, got_q.shape, want_q.shape)
+        assert np.array_equal(got_w, want_w), f"window rows differ: max abs {np.abs(got_w - want_w).max()}"
+        assert np.array_equal(got_q, want_q), f"query rows differ: max abs {np.abs(got_q - want_q).max()}"
