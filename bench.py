@@ -448,14 +448,14 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     pass_ms = e0.elapsed_time(e1) / reps
-    if rank == 0:
-        # the timed regions above last tens of milliseconds; keep the same step running for ~0.6 s more so that
-        # the 100 ms clock / throttle-reason sampler sees the device under exactly this load (not reported)
-        t_soak = time.perf_counter()
-        while time.perf_counter() - t_soak < 0.6:
-            for _ in range(20):
-                step_resident()
-            torch.cuda.synchronize()
+    # The timed regions above last tens of milliseconds; keep the same step running for ~0.6 s more so that the
+    # 100 ms clock / throttle-reason sampler sees the device under exactly this load (not reported).  EVERY rank
+    # runs the same fixed number of steps (ms_res is already the max over ranks): in a row-sharded layout each
+    # step contains a collective, so a rank-0-only or wall-clock-bounded loop would deadlock.
+    soak_steps = min(2000, int(600.0 / max(ms_res, 1e-3)) + 1)
+    for _ in range(soak_steps):
+        step_resident()
+    torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
     if rank == 0:
