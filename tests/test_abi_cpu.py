@@ -35,3 +35,22 @@ def test_product_does_not_import_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), fn
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/qpg.h compiles as strict C99 and a plain-C program links against the library (examples/scan_from_c.c)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        import pytest
+        pytest.skip("no gcc")
+    _lib.load()
+    exe = str(tmp_path / "scan_from_c")
+    cmd = [gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I" + os.path.join(ROOT, "include"),
+           os.path.join(ROOT, "examples", "scan_from_c.c"), "-L" + os.path.join(ROOT, "qpgesture_b200"), "-lqpg_sm100",
+           "-L/usr/local/cuda/lib64", "-lcudart", "-Wl,-rpath," + os.path.join(ROOT, "qpgesture_b200"), "-o", exe]
+    out = subprocess.run(cmd, capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    assert os.path.isfile(exe)
