@@ -110,3 +110,41 @@ def test_layout_planner():
         rs, cg = plan_layout(3_000_000_000, w)
         assert rs * cg == w
     assert [shard_sequences(10, 4, r) for r in range(4)] == [(0, 2), (2, 5), (5, 7), (7, 10)]
+
+
+@pytest.mark.parametrize("path", CASES)
+def test_product_numpy_tail_reproduces_reference_codes(path):
+    """CodeKNN._tail_numpy_segment (product host code, tail='numpy') driven by oracle tables through a stub
+    database reproduces the reference's end-to-end knn_pred: the state machine itself is checked on CPU."""
+    from types import SimpleNamespace
+
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import PAIR_DTYPE, phase_frame  # noqa: F401
+    from tests._common import oracle_db, oracle_queries
+
+    fx, train, test, code, sig = load_case(path)
+    odb = oracle_db("A", train, code, sig)
+    aq, tq = oracle_queries("A", test)
+    aud_k, txt_k = [6 * m for m in range(26)], [8 * m for m in range(26)]
+    stub = SimpleNamespace(
+        pos_rank_host=pos_rank_table(sig), freq_rank_host=fx["freq_rank"].astype(np.int32),
+        phase_amp_host=phase_to_dense(train["phase"]),
+        payload=lambda w: code[int(w) // 26, int(w) % 26:int(w) % 26 + 4],
+        aux=lambda w, which: [int(w) // 26, (aud_k if which == "audio" else txt_k)[int(w) % 26]])
+    knn = SimpleNamespace(db=stub)
+
+    def table(fn, q):
+        t = np.zeros((8, 512), dtype=PAIR_DTYPE)
+        for s in range(8):
+            t["d"][s], t["id"][s] = fn(odb, q[s])
+        return t
+
+    np.random.seed(123456)
+    code0, ph0 = om.init_code_phase(odb)
+    got = []
+    for g in range(aq.shape[0]):
+        codes, phases, _ = CodeKNN._tail_numpy_segment(knn, table(om.audio_table, aq[g]), table(om.text_table, tq[g]),
+                                                       code0, ph0)
+        got.append(codes)
+        code0, ph0 = int(codes[-1]), phases[-1]
+    assert np.array_equal(np.array(got), fx["knn_pred"])
