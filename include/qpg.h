@@ -113,6 +113,72 @@ int qpg_cand_cosine2_minbycode(const float* packed, const double* row_sqnorm1, c
                                const int32_t* labels, int64_t W, int D1, int D2, int64_t id_offset,
                                const float* q, int Q, qpg_pair_t* table1, qpg_pair_t* table2, void* stream);
 
+/* ---------------- one-pass scan for up to 64 query steps (int8-sliced table, tcgen05 kind::i8) -------------
+ * The hot path of the matcher: ALL query steps of a clip against the window table in ONE pass over HBM
+ * (csrc/sliced_scan.cu explains the arithmetic).  The table is kept twice: the float32 tiles of
+ * qpg_pack_rows_f32 (exact re-evaluation, single-query API) and an int8-"sliced" 31-bit fixed-point copy
+ * whose rows are ordered by start code (bin order):
+ *   order[pos]     = source row of sorted position pos (rows with a label outside [0,512) last)
+ *   bin_start[c]   = first sorted position of start code c, c = 0..512
+ * Replaces one search_audio_cands + one search_text_cands call per query step (GestureKNN.py:549-566,
+ * :666-721) for every step of a clip at once; results are the same (distance, id) tables.  Distances of
+ * bins that needed no decision are the filter value (within 2e-7 of the float64 one); ids and the rank
+ * transform are exact.
+ */
+typedef struct {
+  double sq;   /* |q|^2, float64, fixed summation order          */
+  double g;    /* 2^eq / |q|   (0 for an all-zero query)         */
+  double h;    /* query part of the error bound (integer units)  */
+  int32_t ex;  /* eq: |q'| < 2^eq                                */
+  int32_t pad;
+} qpg_qinfo_t;
+typedef struct {
+  double lo, hi;  /* interval that contains the bin's exact minimum distance (lo == hi: exact) */
+  int64_t id;     /* global window id of the only row that can attain it, -1 = empty bin       */
+  int32_t n;
+  int32_t flags;  /* bit 0: lo/hi are the exact float64 distance                               */
+} qpg_bin_t;
+typedef struct {
+  const int8_t* db_slices; /* qpg_slice_rows_i8 output of this feature block   */
+  const int8_t* q_slices;  /* qpg_slice_queries_i8 output (same n_pad)         */
+  int64_t* sacc;           /* int64 [n_pad][ceil(W/128)*128], zeroed by caller */
+  int32_t n_kblocks;       /* ceil(D/128)                                      */
+  int32_t pad;
+} qpg_sliced_seg_t;
+size_t qpg_sliced_bytes(int64_t n_rows, int D);
+size_t qpg_sliced_query_bytes(int D, int n_pad);
+/* rows float32 [W, D] row-major; col_exp int8 [D] optional per-column power-of-two scaling (database rows
+ * are multiplied by 2^-col_exp, queries by 2^+col_exp: the dot product is unchanged, outlier feature
+ * dimensions stop dominating the fixed-point range); row_sqnorm float64 [W] indexed by SOURCE row;
+ * row_info 16 bytes per sorted row (opaque).  slices must be 1024-byte aligned. */
+int qpg_slice_rows_i8(const float* rows, int64_t W, int D, const int32_t* order, const int8_t* col_exp,
+                      const double* row_sqnorm, int8_t* slices, void* row_info, void* stream);
+/* q float32 [Q, ldq]; n_pad in {16,32,48,64} >= Q */
+int qpg_slice_queries_i8(const float* q, int Q, int D, int64_t ldq, const int8_t* col_exp, int n_pad,
+                         int8_t* q_slices, qpg_qinfo_t* q_info, void* stream);
+/* the pass itself: 1 or 2 feature blocks (audio, text) of the same W rows in one launch (stream-K over
+ * row tiles x k-blocks, int64 global accumulation: exact and order independent) */
+int qpg_sliced_scan_i8(const qpg_sliced_seg_t* segs, int n_segs, int64_t W, int n_pad, int nq, void* stream);
+/* CUDA-core evaluation of the same integer sums from the same tile images (tests / debugging): queries
+ * 0, q_stride, 2*q_stride, ... < nq only */
+int qpg_sliced_scan_ref(const int8_t* db_slices, const int8_t* q_slices, int n_kblocks, int64_t W, int n_pad, int nq,
+                        int q_stride, int64_t* sacc, void* stream);
+/* per (query, start code) records from sacc; bins with more than one possible winner are re-evaluated in
+ * float64 right here.  packed/row_sqnorm: float32 tile table + norms; source row r of this (sliced) shard is row
+ * r + row_base there and has global window id id_offset + r.
+ * stats (optional, uint64[2]): [0] += rows re-evaluated here, [1] += bins decided in qpg_sliced_resolve */
+int qpg_sliced_bins(const int64_t* sacc, int64_t W, int nq, const int32_t* bin_start, const void* row_info,
+                    const int32_t* order, const double* row_sqnorm, int64_t id_offset, int64_t row_base,
+                    const qpg_qinfo_t* q_info, const float* packed, int D, const float* q, int64_t ldq,
+                    qpg_bin_t* bins_out, uint64_t* stats, void* stream);
+/* merge n_parts record sets (row shards), decide cross-shard winners and overlapping bins in float64, emit the
+ * final table, its stable rank transform (= qpg_rank512) and per-query flags (bit 0: exact tie between
+ * non-empty bins, i.e. the reference's argsort order is platform defined there).  Part p, query q, code c is
+ * parts[p*part_stride + q*512 + c].  packed/row_sqnorm address rows by (global id - first_id). */
+int qpg_sliced_resolve(const qpg_bin_t* parts, int n_parts, int64_t part_stride, int nq, const float* packed, int D,
+                       const double* row_sqnorm, int64_t first_id, const qpg_qinfo_t* q_info, const float* q,
+                       int64_t ldq, qpg_pair_t* table, int32_t* ranks, int32_t* qflags, uint64_t* stats, void* stream);
+
 /* ---------------- candidate distance, Levenshtein, fused min-by-code -----
  * tokens [W, 12] uint32 (11 used: g0*320+g1 per tap, GestureKNN.py:58-60),
  * q_tokens [Q, 12].  dist = unit-cost edit distance (Levenshtein.distance,
@@ -144,6 +210,9 @@ int qpg_table_merge(const qpg_pair_t* parts, int n_parts, int64_t n_entries, qpg
  * exact ties, which NumPy leaves platform-defined.
  */
 int qpg_rank512(const qpg_pair_t* table, int Q, int32_t* ranks, void* stream);
+/* same, plus qflags[q] = 1 when two non-empty bins of step q hold exactly the same distance (NumPy's order of
+ * those is platform defined; typical for the integer Levenshtein distances of mode B) */
+int qpg_rank512_ties(const qpg_pair_t* table, int Q, int32_t* ranks, int32_t* qflags, void* stream);
 
 /* ---------------- sequential tail of search_code_knn ----------------------
  * One thread block per clip walks its n_seg*8 steps (GestureKNN.py:528-660,
@@ -182,6 +251,24 @@ int qpg_match_tail_segments(const qpg_pair_t* aud_table, const qpg_pair_t* txt_t
                             int64_t* codes_out, int32_t* vote_out, float* phase_out, int32_t* status_out,
                             void* stream);
 
+/* ---------------- sequential tail, split into a parallel lookup and a short walk (csrc/match_walk.cu) -------
+ * qpg_match_lookup: for every query step q < Q and every possible previous code `last` the two arg-mins of
+ * GestureKNN.py:540-555,:574-576 and what hangs off the chosen windows, as 32-byte entries [Q][512].
+ * pos_rank_t is the TRANSPOSED pose rank table, int16 [512 c][512 last]; ranks/tables as produced by
+ * qpg_rank512 / qpg_sliced_resolve; qflags_* (optional) per-step tie flags of qpg_sliced_resolve.
+ * qpg_match_walk: one thread block per clip follows the entries (GestureKNN.py:627-660, segments chained as
+ * :791,:800).  codes_out is pre-filled with -1, so a clip that stops early is recognisable.
+ * status_out[clip]: bit 0 (1) = a chosen start code had no window (the reference raises IndexError at :631);
+ *                   bit 1 (2) = the result depended on the order of exact ties, which the reference leaves to
+ *                   NumPy's unstable argsort (this implementation: lower code first). */
+int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, const int32_t* aud_rank,
+                     const int32_t* txt_rank, const int16_t* pos_rank_t, const int32_t* freq_rank, const int32_t* code,
+                     int64_t n_seq, const int32_t* aud_frame, const int32_t* txt_frame, const int32_t* qflags_a,
+                     const int32_t* qflags_t, int Q, void* entries, void* stream);
+int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp, const int32_t* seed_code,
+                   const float* seed_phase, int n_clips, int n_seg, int64_t* codes_out, int32_t* vote_out,
+                   float* phase_out, int32_t* status_out, void* stream);
+
 /* ---------------- VQ codebook L2 argmin -----------------------------------
  * BottleneckBlock.quantise (codebook/models/bottleneck.py:120-126):
  *   dist[m][k] = fl32( fl32(|x_m|^2 - 2*<x_m,c_k>) + |c_k|^2 ),  idx = first argmin
@@ -202,7 +289,7 @@ int qpg_vq_dequantise_f32(const int64_t* idx, const float* codebook, int64_t M, 
  * Covers nn.Conv1d (encdec.py:20,24,39,113; resnet.py:33-36) and, as two
  * output phases, nn.ConvTranspose1d k4 s2 p1 (encdec.py:45).
  * w is [n_taps, Cin, Cout] float32 (repacked from torch's [Cout, Cin, k]).
- * precision: 0 = float32 FFMA (parity mode), 1 = 3xTF32 tensor cores.
+ * precision: must be 0 (float32 FFMA, the index-parity mode); the tensor-core path is qpg_conv1d_taps_tf32.
  */
 typedef struct {
   int B, T_in, T_out_total, C_in, C_out;

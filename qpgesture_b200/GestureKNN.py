@@ -53,8 +53,9 @@ def build_parser() -> argparse.ArgumentParser:
     # additions (not in the reference)
     p.add_argument("--mode", choices=("A", "B"), default="A",
                    help="A = WavLM cosine (the literals shipped at GestureKNN.py:842-843), B = wavvq Levenshtein")
-    p.add_argument("--tail", choices=("device", "numpy"), default="device",
-                   help="where the 512-element sequential tail runs (numpy = the reference's own argsort calls)")
+    p.add_argument("--tail", choices=("auto", "device", "numpy"), default="auto",
+                   help="auto = device tail, clips whose result hinged on the order of exact ties are redone with the "
+                        "reference's own NumPy argsort calls; device = stable order everywhere; numpy = NumPy tail")
     p.add_argument("--gpu", type=int, default=0)
     return p
 
@@ -108,7 +109,7 @@ class CodeKNN(object):
                  speech_features=None, speech_features_feat=None, wavvq_train_feat=None, phase_train=None,
                  context_train=None, use_wavlm=False, use_wavvq=False, use_phase=False, use_txt=False, *,
                  codebook_signature=None, train_codebook=None, device=None, database: Optional[MatchDatabase] = None,
-                 seq_range=None, process_group=None, tail="device", aud_rows=None, aud_tokens=None):
+                 seq_range=None, process_group=None, tail="auto", aud_rows=None, aud_tokens=None):
         super().__init__()
         self.use_phase = use_phase
         self.phase_channels = 8
@@ -182,22 +183,26 @@ class CodeKNN(object):
             t = db.txt if which == "text" else db.aud
             assert q.dtype == torch.float32 and q.shape[1] == t.D, (q.shape, t.D)
             _lib.check(lib.qpg_cand_cosine_minbycode_team(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
-                                                          t.W, t.D, db.id_offset, _lib.ptr(q), Q, _lib.ptr(table), 0,
+                                                          t.W, t.D, db.exact_offset, _lib.ptr(q), Q, _lib.ptr(table), 0,
                                                           self._team_size(t.D), sp),
                        "qpg_cand_cosine_minbycode_team")
         else:
             assert q.dtype == torch.int32 and q.shape[1] == 12
             _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W, db.id_offset,
                                                   _lib.ptr(q), Q, _lib.ptr(table), sp), "qpg_cand_lev_minbycode")
-        if self.process_group is not None:
+        if self._sharded_exact():
             table = self._merge_shards(table, stream)
         return table
+
+    def _sharded_exact(self) -> bool:
+        """True when the float32 tables hold only this rank's rows, i.e. exact scans need the cross-rank merge."""
+        return self.process_group is not None and not self.db.replicated
 
     def _team_size(self, D: int) -> int:
         """Team size S for the cosine scan.  Single GPU: 0 (library picks).  Row-sharded: every rank must
         use the same S (it fixes the float64 summation order, see qpg_cand_cosine_minbycode_team), so it is
         derived from the largest shard of the WHOLE database, not from this rank's row count."""
-        if self.process_group is None:
+        if not self._sharded_exact():
             return 0
         import torch.distributed as dist
 
@@ -279,47 +284,82 @@ class CodeKNN(object):
 
     # ---- preallocated plan: the whole step as a fixed launch sequence (optionally one CUDA graph) ------
     def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False,
-                  overlap_tail: bool = False, fused_scan: bool = True):
+                  engine: Optional[str] = None):
         """Static device buffers for `n_clips` clips x `n_seg` segments.  `tail_clips` = slice of the
         clips whose sequential tail this rank runs (default: all).  Fill plan.qa / plan.qt /
-        plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes."""
+        plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes / plan.status.
+
+        engine "sliced" (default in mode A): every query step of the batch in ONE pass over the int8-sliced
+        table per 64 steps (tcgen05 kind::i8) + interval logic + float64 re-evaluation of undecided bins;
+        engine "f64": the float64 streaming scans of round 1 (4 steps per pass; the only engine of mode B)."""
         dev, db = self.db.device, self.db
         Q = n_clips * n_seg * STEPS_PER_SEGMENT
         tc = tail_clips if tail_clips is not None else slice(0, n_clips)
         n_tail = tc.stop - tc.start
-        p = SimpleNamespace(n_clips=n_clips, n_seg=n_seg, Q=Q, tail=tc, n_tail=n_tail, graph=None)
-        # optional (single clip, single GPU): overlap each segment's rank + tail with the scans of the following
-        # segments on a side stream.  Measured slower than one 12-pass scan call + one tail once the text scan was
-        # fused (0.989 vs 0.915 ms/step), so it is off by default.
-        p.overlap = bool(overlap_tail) and n_clips == 1 and n_tail == 1 and self.process_group is None
+        if engine is None:
+            engine = "sliced" if (db.mode == "A" and db.aud_s is not None) else "f64"
+        if engine == "sliced" and (db.mode != "A" or db.aud_s is None):
+            raise ValueError("the sliced engine needs a mode-A database built with sliced=True")
+        if engine == "sliced" and self.process_group is not None and not db.replicated:
+            raise ValueError("row-sharded sliced scans need MatchDatabase(replicate_exact=True)")
+        p = SimpleNamespace(n_clips=n_clips, n_seg=n_seg, Q=Q, tail=tc, n_tail=n_tail, graph=None, engine=engine)
+        world = 1
+        if self.process_group is not None:
+            import torch.distributed as dist
+            world = dist.get_world_size(self.process_group)
+        p.world = world
+        lib = _lib.load()
         with torch.cuda.device(dev):
-            p.side_stream = torch.cuda.Stream(device=dev) if p.overlap else None
-            p.state = torch.zeros((max(n_tail, 1), 8 * 16 + 4), dtype=torch.float32, device=dev)
-            # fused single-pass scan when the audio|text table exists and a warp team split is not needed
-            sms = torch.cuda.get_device_properties(dev).multi_processor_count
-            p.fused = (db.fused is not None and self.process_group is None and fused_scan
-                       and -(-db.W // 8) * 2 >= sms * 12)
-            if p.fused:
-                p.qf = torch.zeros((Q, db.aud.D + db.txt.D), dtype=torch.float32, device=dev)
-                p.qa, p.qt = p.qf[:, :db.aud.D], p.qf[:, db.aud.D:]          # views: copy destinations only
-            elif db.mode == "A":
+            Qt = n_tail * n_seg * STEPS_PER_SEGMENT
+            p.Qt = Qt
+            if db.mode == "A":
                 p.qa = torch.zeros((Q, db.aud.D), dtype=torch.float32, device=dev)
-                p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
             else:
                 p.qa = torch.zeros((Q, 12), dtype=torch.int32, device=dev)
-                p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
+            p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
             p.seed_code = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
             p.seed_phase = torch.zeros((n_clips, 8, 16), dtype=torch.float32, device=dev)
-            p.ta, p.tt = new_table(Q, dev), new_table(Q, dev)
-            if self.process_group is not None:
-                import torch.distributed as dist
-                world = dist.get_world_size(self.process_group)
-                p.parts_a = torch.empty((world, Q, codebook_size, 2), dtype=torch.int64, device=dev)
-                p.parts_t = torch.empty((world, Q, codebook_size, 2), dtype=torch.int64, device=dev)
-                p.ma, p.mt = new_table(Q, dev), new_table(Q, dev)
-            Qt = n_tail * n_seg * STEPS_PER_SEGMENT
+            p.fused = False
+            if engine == "sliced":
+                n_pass = -(-Q // 64)
+                per = -(-Q // n_pass)
+                p.passes = []
+                q0 = 0
+                while q0 < Q:
+                    nq = min(per, Q - q0)
+                    n_pad = -(-nq // 16) * 16
+                    from .matchdb import aligned_bytes
+                    p.passes.append(SimpleNamespace(
+                        q0=q0, nq=nq, n_pad=n_pad,
+                        qs_a=aligned_bytes(lib.qpg_sliced_query_bytes(db.aud.D, n_pad), dev),
+                        qs_t=aligned_bytes(lib.qpg_sliced_query_bytes(db.txt.D, n_pad), dev)))
+                    q0 += nq
+                n_pad_max = max(ps.n_pad for ps in p.passes)
+                p.qinfo_a = torch.zeros((Q, 4), dtype=torch.float64, device=dev)
+                p.qinfo_t = torch.zeros((Q, 4), dtype=torch.float64, device=dev)
+                p.sacc_a = torch.zeros((n_pad_max, db.aud_s.Wpad), dtype=torch.int64, device=dev)
+                p.sacc_t = torch.zeros((n_pad_max, db.txt_s.Wpad), dtype=torch.int64, device=dev)
+                p.bins = torch.zeros((2, Q, codebook_size, 4), dtype=torch.int64, device=dev)      # qpg_bin_t, a then t
+                p.parts = p.bins[None] if world == 1 else \
+                    torch.zeros((world, 2, Q, codebook_size, 4), dtype=torch.int64, device=dev)
+                p.stats = torch.zeros((2,), dtype=torch.int64, device=dev)
+                p.ta, p.tt = new_table(Qt, dev), new_table(Qt, dev)
+            else:
+                p.fused = db.fused is not None and not self._sharded_exact() and \
+                    -(-db.fused.W // 8) * 2 >= torch.cuda.get_device_properties(dev).multi_processor_count * 12
+                if p.fused:
+                    p.qf = torch.zeros((Q, db.aud.D + db.txt.D), dtype=torch.float32, device=dev)
+                p.fa, p.ft = new_table(Q, dev), new_table(Q, dev)                 # tables of all Q steps
+                if self._sharded_exact():
+                    p.parts_f = torch.empty((world, 2, Q, codebook_size, 2), dtype=torch.int64, device=dev)
+                    p.both = torch.empty((2, Q, codebook_size, 2), dtype=torch.int64, device=dev)
+                    p.fa, p.ft = p.both[0], p.both[1]
+                    p.merged = torch.empty((2, Q, codebook_size, 2), dtype=torch.int64, device=dev)
             p.ra = torch.empty((Qt, codebook_size), dtype=torch.int32, device=dev)
             p.rt = torch.empty((Qt, codebook_size), dtype=torch.int32, device=dev)
+            p.qfa = torch.zeros((Qt,), dtype=torch.int32, device=dev)
+            p.qft = torch.zeros((Qt,), dtype=torch.int32, device=dev)
+            p.entries = torch.empty((max(Qt, 1), codebook_size, 4), dtype=torch.int64, device=dev)   # 32-byte entries
             p.codes = torch.empty((n_tail, n_seg, num_frames_code), dtype=torch.int64, device=dev)
             p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
             p.status = torch.zeros((n_tail,), dtype=torch.int32, device=dev)
@@ -337,100 +377,99 @@ class CodeKNN(object):
     def _scan_fused(self, q, ta, tt, nq, sp):
         lib, db = _lib.load(), self.db
         _lib.check(lib.qpg_cand_cosine2_minbycode(_lib.ptr(db.fused.packed), _lib.ptr(db.aud.sqnorm), _lib.ptr(db.txt.sqnorm),
-                                                  _lib.ptr(db.labels), db.W, db.aud.D, db.txt.D, db.id_offset, _lib.ptr(q),
-                                                  nq, _lib.ptr(ta), _lib.ptr(tt), sp), "qpg_cand_cosine2_minbycode")
+                                                  _lib.ptr(db.labels), db.fused.W, db.aud.D, db.txt.D, db.exact_offset,
+                                                  _lib.ptr(q), nq, _lib.ptr(ta), _lib.ptr(tt), sp),
+                   "qpg_cand_cosine2_minbycode")
 
-    def _launch_plan_overlapped(self, p):
-        """Single clip, single GPU: segment g's ranks + tail run on a side stream (one SM is left free for
-        them) while the main stream already scans segment g+1.  Same kernels, same results."""
+    def _launch_sliced(self, p, sp):
+        """slice queries -> one tensor-core pass per <= 64 steps -> per-bin records -> [all-gather] -> resolve."""
         lib, db = _lib.load(), self.db
-        main = torch.cuda.current_stream()
-        side = p.side_stream
-        sms = torch.cuda.get_device_properties(db.device).multi_processor_count
-        S8 = STEPS_PER_SEGMENT
-        sp = _lib.stream_ptr(main)
-        _lib.check(lib.qpg_table_init(_lib.ptr(p.ta), p.Q * codebook_size, sp), "qpg_table_init")
-        _lib.check(lib.qpg_table_init(_lib.ptr(p.tt), p.Q * codebook_size, sp), "qpg_table_init")
-        lib.qpg_tune_cosine(0, 0, sms - 1, 0)
-        try:
-            for g in range(p.n_seg):
-                qs = slice(g * S8, (g + 1) * S8)
-                scans = () if p.fused else (("audio", p.qa[qs], p.ta[qs]), ("text", p.qt[qs], p.tt[qs]))
-                if p.fused:
-                    self._scan_fused(p.qf[qs], p.ta[qs], p.tt[qs], S8, sp)
-                for which, q, tab in scans:
-                    if which == "text" or db.mode == "A":
-                        t = db.txt if which == "text" else db.aud
-                        _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm),
-                                                                 _lib.ptr(db.labels), t.W, t.D, db.id_offset, _lib.ptr(q),
-                                                                 S8, _lib.ptr(tab), 0, sp), "qpg_cand_cosine_minbycode")
-                    else:
-                        _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W,
-                                                              db.id_offset, _lib.ptr(q), S8, _lib.ptr(tab), sp),
-                                   "qpg_cand_lev_minbycode")
-                ev = torch.cuda.Event()
-                ev.record(main)
-                side.wait_event(ev)
-                with torch.cuda.stream(side):
-                    ss = _lib.stream_ptr(side)
-                    _lib.check(lib.qpg_rank512(_lib.ptr(p.ta[qs]), S8, _lib.ptr(p.ra[qs]), ss), "qpg_rank512")
-                    _lib.check(lib.qpg_rank512(_lib.ptr(p.tt[qs]), S8, _lib.ptr(p.rt[qs]), ss), "qpg_rank512")
-                    _lib.check(lib.qpg_match_tail_segments(
-                        _lib.ptr(p.ta), _lib.ptr(p.tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank),
-                        _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
-                        _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
-                        1, p.n_seg, g, 1, _lib.ptr(p.state), _lib.ptr(p.codes), _lib.ptr(p.vote), _lib.ptr(p.phase),
-                        _lib.ptr(p.status), ss), "qpg_match_tail_segments")
-        finally:
-            lib.qpg_tune_cosine(0, 0, 0, 0)
-        main.wait_stream(side)
+        A, T = db.aud_s, db.txt_s
+        col_a, col_t = _lib.ptr(A.col_exp), _lib.ptr(T.col_exp)
+        for ps in p.passes:
+            qa, qt = p.qa[ps.q0:ps.q0 + ps.nq], p.qt[ps.q0:ps.q0 + ps.nq]
+            qia, qit = p.qinfo_a[ps.q0:ps.q0 + ps.nq], p.qinfo_t[ps.q0:ps.q0 + ps.nq]
+            _lib.check(lib.qpg_slice_queries_i8(_lib.ptr(qa), ps.nq, A.D, A.D, col_a, ps.n_pad, _lib.ptr(ps.qs_a),
+                                                _lib.ptr(qia), sp), "qpg_slice_queries_i8")
+            _lib.check(lib.qpg_slice_queries_i8(_lib.ptr(qt), ps.nq, T.D, T.D, col_t, ps.n_pad, _lib.ptr(ps.qs_t),
+                                                _lib.ptr(qit), sp), "qpg_slice_queries_i8")
+            p.sacc_a.zero_()
+            p.sacc_t.zero_()
+            segs = (_lib.SlicedSeg * 2)()
+            segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = \
+                A.slices.data_ptr(), ps.qs_a.data_ptr(), p.sacc_a.data_ptr(), A.n_kblocks
+            segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = \
+                T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
+            _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "qpg_sliced_scan_i8")
+            for x, (S, E, sacc, q, qi) in enumerate(((A, db.aud, p.sacc_a, qa, qia), (T, db.txt, p.sacc_t, qt, qit))):
+                _lib.check(lib.qpg_sliced_bins(_lib.ptr(sacc), S.W, ps.nq, _lib.ptr(S.bin_start), _lib.ptr(S.row_info),
+                                               _lib.ptr(S.order), _lib.ptr(E.sqnorm), db.id_offset, db.row_base,
+                                               _lib.ptr(qi), _lib.ptr(E.packed), S.D, _lib.ptr(q), S.D,
+                                               _lib.ptr(p.bins[x, ps.q0:ps.q0 + ps.nq]), _lib.ptr(p.stats), sp),
+                           "qpg_sliced_bins")
+        if p.world > 1:
+            import torch.distributed as dist
+            dist.all_gather_into_tensor(p.parts, p.bins, group=self.process_group)     # the ONE data-path collective
+        per_clip = p.n_seg * STEPS_PER_SEGMENT
+        q0, q1 = p.tail.start * per_clip, p.tail.stop * per_clip
+        stride = 2 * p.Q * codebook_size                                               # records between two parts
+        for x, (E, q, qi, tab, rk, qf) in enumerate(((db.aud, p.qa, p.qinfo_a, p.ta, p.ra, p.qfa),
+                                                     (db.txt, p.qt, p.qinfo_t, p.tt, p.rt, p.qft))):
+            parts = p.parts[0, x, q0:q1]
+            _lib.check(lib.qpg_sliced_resolve(_lib.ptr(parts), p.world, stride, q1 - q0, _lib.ptr(E.packed), E.D,
+                                              _lib.ptr(E.sqnorm), db.exact_offset, _lib.ptr(qi[q0:q1]), _lib.ptr(q[q0:q1]),
+                                              E.D, _lib.ptr(tab), _lib.ptr(rk), _lib.ptr(qf), _lib.ptr(p.stats), sp),
+                       "qpg_sliced_resolve")
+        return p.ta, p.tt
 
-    def _launch_plan(self, p):
-        if getattr(p, "overlap", False):
-            return self._launch_plan_overlapped(p)
+    def _launch_f64(self, p, sp):
+        """round-1 float64 streaming scans (exact distances everywhere) + stable ranks with tie flags."""
         lib, db = _lib.load(), self.db
-        sp = _lib.stream_ptr()
         if p.fused:
-            _lib.check(lib.qpg_table_init(_lib.ptr(p.ta), p.Q * codebook_size, sp), "qpg_table_init")
-            _lib.check(lib.qpg_table_init(_lib.ptr(p.tt), p.Q * codebook_size, sp), "qpg_table_init")
-            self._scan_fused(p.qf, p.ta, p.tt, p.Q, sp)
-        for which, q, tab in (() if p.fused else (("audio", p.qa, p.ta), ("text", p.qt, p.tt))):
+            p.qf[:, :db.aud.D].copy_(p.qa)
+            p.qf[:, db.aud.D:].copy_(p.qt)
+            _lib.check(lib.qpg_table_init(_lib.ptr(p.fa), p.Q * codebook_size, sp), "qpg_table_init")
+            _lib.check(lib.qpg_table_init(_lib.ptr(p.ft), p.Q * codebook_size, sp), "qpg_table_init")
+            self._scan_fused(p.qf, p.fa, p.ft, p.Q, sp)
+        for which, q, tab in (() if p.fused else (("audio", p.qa, p.fa), ("text", p.qt, p.ft))):
             _lib.check(lib.qpg_table_init(_lib.ptr(tab), p.Q * codebook_size, sp), "qpg_table_init")
             if which == "text" or db.mode == "A":
                 t = db.txt if which == "text" else db.aud
                 _lib.check(lib.qpg_cand_cosine_minbycode_team(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels),
-                                                              t.W, t.D, db.id_offset, _lib.ptr(q), p.Q, _lib.ptr(tab), 0,
+                                                              t.W, t.D, db.exact_offset, _lib.ptr(q), p.Q, _lib.ptr(tab), 0,
                                                               self._team_size(t.D), sp), "qpg_cand_cosine_minbycode_team")
             else:
                 _lib.check(lib.qpg_cand_lev_minbycode(_lib.ptr(db.tokens), _lib.ptr(db.labels), db.W, db.id_offset,
                                                       _lib.ptr(q), p.Q, _lib.ptr(tab), sp), "qpg_cand_lev_minbycode")
-        ta, tt = p.ta, p.tt
-        if self.process_group is not None:
+        fa, ft = p.fa, p.ft
+        if self._sharded_exact():
             import torch.distributed as dist
-            world = dist.get_world_size(self.process_group)
-            dist.all_gather_into_tensor(p.parts_a, p.ta, group=self.process_group)
-            dist.all_gather_into_tensor(p.parts_t, p.tt, group=self.process_group)
-            for parts, out in ((p.parts_a, p.ma), (p.parts_t, p.mt)):
-                _lib.check(lib.qpg_table_merge(_lib.ptr(parts), world, p.Q * codebook_size, _lib.ptr(out), sp),
-                           "qpg_table_merge")
-            ta, tt = p.ma, p.mt
+            dist.all_gather_into_tensor(p.parts_f, p.both, group=self.process_group)   # both tables, one collective
+            _lib.check(lib.qpg_table_merge(_lib.ptr(p.parts_f), p.world, 2 * p.Q * codebook_size, _lib.ptr(p.merged), sp),
+                       "qpg_table_merge")
+            fa, ft = p.merged[0], p.merged[1]
         per_clip = p.n_seg * STEPS_PER_SEGMENT
         q0, q1 = p.tail.start * per_clip, p.tail.stop * per_clip
-        ta_s, tt_s = ta[q0:q1], tt[q0:q1]
-        Qt = q1 - q0
-        _lib.check(lib.qpg_rank512(_lib.ptr(ta_s), Qt, _lib.ptr(p.ra), sp), "qpg_rank512")
-        _lib.check(lib.qpg_rank512(_lib.ptr(tt_s), Qt, _lib.ptr(p.rt), sp), "qpg_rank512")
-        # the scans streamed the whole table through L2: re-warm what the tail reads with dependent loads
-        for t_ in (db.pos_rank, db.code, db.phase_amp):
-            nbytes = t_.numel() * t_.element_size()
-            if nbytes <= (32 << 20):
-                _lib.check(lib.qpg_l2_prefetch(_lib.ptr(t_), nbytes, sp), "qpg_l2_prefetch")
+        ta, tt = fa[q0:q1], ft[q0:q1]
+        _lib.check(lib.qpg_rank512_ties(_lib.ptr(ta), q1 - q0, _lib.ptr(p.ra), _lib.ptr(p.qfa), sp), "qpg_rank512_ties")
+        _lib.check(lib.qpg_rank512_ties(_lib.ptr(tt), q1 - q0, _lib.ptr(p.rt), _lib.ptr(p.qft), sp), "qpg_rank512_ties")
+        p.ta, p.tt = ta, tt
+        return ta, tt
+
+    def _launch_plan(self, p):
+        lib, db = _lib.load(), self.db
+        sp = _lib.stream_ptr()
+        ta, tt = self._launch_sliced(p, sp) if p.engine == "sliced" else self._launch_f64(p, sp)
+        if p.Qt == 0:
+            return
         sc, sph = p.seed_code[p.tail], p.seed_phase[p.tail]
-        _lib.check(lib.qpg_match_tail(_lib.ptr(ta_s), _lib.ptr(tt_s), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank),
-                                      _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
-                                      _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(sc), _lib.ptr(sph),
-                                      p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote), _lib.ptr(p.phase),
-                                      _lib.ptr(p.status), sp), "qpg_match_tail")
+        _lib.check(lib.qpg_match_lookup(_lib.ptr(ta), _lib.ptr(tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank_t),
+                                        _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame),
+                                        _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft), p.Qt,
+                                        _lib.ptr(p.entries), sp), "qpg_match_lookup")
+        _lib.check(lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
+                                      _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote),
+                                      _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
 
     def run_plan(self, p):
         """Enqueue one step on the current stream (graph replay when the plan was captured)."""
@@ -443,7 +482,8 @@ class CodeKNN(object):
 
     # ---- sequential tail ---------------------------------------------------------
     def tail_device(self, ta, tt, seed_code, seed_phase, n_clips, n_seg, want_phase=True):
-        """ranks + match_tail kernels for n_clips x n_seg x 8 steps already scanned."""
+        """rank + lookup + walk kernels for n_clips x n_seg x 8 steps already scanned.
+        -> (codes, vote, phase, status); status bit 0: IndexError of GestureKNN.py:631, bit 1: tie dependent."""
         lib, db, dev = _lib.load(), self.db, self.db.device
         Q = n_clips * n_seg * STEPS_PER_SEGMENT
         assert ta.shape[0] == Q and tt.shape[0] == Q
@@ -451,20 +491,25 @@ class CodeKNN(object):
             sp = _lib.stream_ptr()
             ra = torch.empty((Q, codebook_size), dtype=torch.int32, device=dev)
             rt = torch.empty((Q, codebook_size), dtype=torch.int32, device=dev)
-            _lib.check(lib.qpg_rank512(_lib.ptr(ta), Q, _lib.ptr(ra), sp), "qpg_rank512")
-            _lib.check(lib.qpg_rank512(_lib.ptr(tt), Q, _lib.ptr(rt), sp), "qpg_rank512")
+            qfa = torch.empty((Q,), dtype=torch.int32, device=dev)
+            qft = torch.empty((Q,), dtype=torch.int32, device=dev)
+            _lib.check(lib.qpg_rank512_ties(_lib.ptr(ta), Q, _lib.ptr(ra), _lib.ptr(qfa), sp), "qpg_rank512_ties")
+            _lib.check(lib.qpg_rank512_ties(_lib.ptr(tt), Q, _lib.ptr(rt), _lib.ptr(qft), sp), "qpg_rank512_ties")
             sc = torch.as_tensor(np.asarray(seed_code, dtype=np.int32).reshape(n_clips), device=dev)
             sph = torch.as_tensor(np.ascontiguousarray(seed_phase, dtype=np.float32).reshape(n_clips, 8, 16), device=dev)
+            entries = torch.empty((Q, codebook_size, 4), dtype=torch.int64, device=dev)
             codes = torch.empty((n_clips, n_seg, num_frames_code), dtype=torch.int64, device=dev)
             vote = torch.empty((n_clips, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
             status = torch.empty((n_clips,), dtype=torch.int32, device=dev)
             phase = torch.empty((n_clips, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
                 if want_phase else None
-            _lib.check(lib.qpg_match_tail(_lib.ptr(ta), _lib.ptr(tt), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(db.pos_rank),
-                                          _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.phase_amp),
-                                          _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(sc), _lib.ptr(sph),
-                                          n_clips, n_seg, _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(phase),
-                                          _lib.ptr(status), sp), "qpg_match_tail")
+            _lib.check(lib.qpg_match_lookup(_lib.ptr(ta), _lib.ptr(tt), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(db.pos_rank_t),
+                                            _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame),
+                                            _lib.ptr(db.txt_frame), _lib.ptr(qfa), _lib.ptr(qft), Q, _lib.ptr(entries), sp),
+                       "qpg_match_lookup")
+            _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
+                                          _lib.ptr(sph), n_clips, n_seg, _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(phase),
+                                          _lib.ptr(status), sp), "qpg_match_walk")
         return codes, vote, phase, status
 
     def _tail_numpy_segment(self, ta_np, tt_np, seed_code, seed_phase, desired_k=0, use_txt=True, use_aud=True):
@@ -530,21 +575,32 @@ class CodeKNN(object):
         ctx = np.asarray(clip_context)
         txt_q = ctx[[int(i / denom * 30) for i in i_list]]
         ta, tt = self.match_tables(aud_q, txt_q)
-        if self.tail == "device" and use_aud and use_txt and len(i_list) == STEPS_PER_SEGMENT:
+        if self.tail in ("device", "auto") and use_aud and use_txt and len(i_list) == STEPS_PER_SEGMENT:
             codes, vote, phase, status = self.tail_device(ta, tt, [init_code], np.asarray(init_phase_amp)[None], 1, 1)
-            if int(status.cpu()[0]) != 0:
-                raise IndexError("list index out of range")           # same failure as GestureKNN.py:631
-            return codes[0, 0].cpu().numpy(), phase[0, 0].cpu().numpy(), vote[0, 0].cpu().numpy()
+            st = int(status.cpu()[0])
+            self.last_status = np.array([st])
+            if not (st & 2 and self.tail == "auto"):                  # tie dependent -> NumPy's own order below
+                if st & 1:
+                    raise IndexError("list index out of range")       # same failure as GestureKNN.py:631
+                return codes[0, 0].cpu().numpy(), phase[0, 0].cpu().numpy(), vote[0, 0].cpu().numpy()
         return self._tail_numpy_segment(table_to_numpy(ta), table_to_numpy(tt), init_code, init_phase_amp,
                                         desired_k, use_txt=use_txt, use_aud=use_aud)
 
     # ---- batched entry: many clips at once ---------------------------------------
     def match_clips(self, aud_q, txt_q, seed_code=None, seed_phase=None, tail=None, out=None, sync=True,
-                    tail_clips=None):
+                    tail_clips=None, status_out=None, engine=None):
         """aud_q [n_clips, n_seg, 8, Da] (or tokens [..., 11|22]), txt_q [n_clips, n_seg, 8, Dt]: host NumPy
         arrays or (pinned) host torch tensors.  Returns int64 codes [n_clips, n_seg, 30] on the host.
-        With `out` (a pinned int64 host tensor) and sync=False the call only enqueues H2D copies, the
-        captured step and the D2H copy on the current stream (the caller synchronises)."""
+
+        tail: "auto" (default) = device tail; clips whose result depended on the order of exact ties are
+        redone with the reference's own NumPy calls (`_tail_numpy_segment`) so that the platform's argsort
+        order applies as it does in the reference; "device" = stable order (lower code first) everywhere;
+        "numpy" = NumPy tail for every clip.  A chosen start code without window raises IndexError as
+        GestureKNN.py:631 does.
+
+        With `out` (+ `status_out`, pinned int64 / int32 host tensors) and sync=False the call only enqueues
+        the H2D copies, the captured step and the D2H copies on the current stream: the caller synchronises
+        and MUST look at status_out (bit 0: IndexError, bit 1: tie dependent) - rows of failed clips are -1."""
         tail = tail or self.tail
         is_t = isinstance(aud_q, torch.Tensor)
         n_clips, n_seg = aud_q.shape[0], aud_q.shape[1]
@@ -553,11 +609,11 @@ class CodeKNN(object):
             seeds = [self.init_code_phase() for _ in range(n_clips)]
             seed_code = [s[0] for s in seeds]
             seed_phase = np.stack([s[1] for s in seeds])
-        if tail == "device":
-            key = (n_clips, n_seg, None if tail_clips is None else (tail_clips.start, tail_clips.stop))
+        if tail in ("device", "auto"):
+            key = (n_clips, n_seg, None if tail_clips is None else (tail_clips.start, tail_clips.stop), engine)
             plans = self.__dict__.setdefault("_plans", {})
             if key not in plans:
-                plans[key] = self.make_plan(n_clips, n_seg, tail_clips=tail_clips)
+                plans[key] = self.make_plan(n_clips, n_seg, tail_clips=tail_clips, engine=engine)
             p = plans[key]
             dev = self.db.device
             with torch.cuda.device(dev):
@@ -578,14 +634,31 @@ class CodeKNN(object):
                 self.run_plan(p)
                 if out is not None:
                     out.copy_(p.codes, non_blocking=True)
+                    if status_out is not None:
+                        status_out.copy_(p.status, non_blocking=True)
                     if not sync:
                         return out
                     torch.cuda.synchronize(dev)
                     codes_h = out.numpy()
+                    status = status_out.numpy() if status_out is not None else p.status.cpu().numpy()
                 else:
                     codes_h = p.codes.cpu().numpy()
-                if int(p.status.max().cpu()) != 0:
+                    status = p.status.cpu().numpy()
+                self.last_status = status.copy()
+                redo = [b for b in range(p.n_tail) if status[b] & 2] if tail == "auto" else []
+                if any((status[b] & 1) and b not in redo for b in range(p.n_tail)):
                     raise IndexError("list index out of range")
+                if redo:                                                  # NumPy's own tie order for these clips
+                    codes_h = np.array(codes_h, copy=True)
+                    ta_np = table_to_numpy(p.ta).reshape(p.n_tail, n_seg, STEPS_PER_SEGMENT, codebook_size)
+                    tt_np = table_to_numpy(p.tt).reshape(p.n_tail, n_seg, STEPS_PER_SEGMENT, codebook_size)
+                    sc_np, sp_np = np.asarray(sc_h), np.asarray(sp_h)
+                    for b in redo:
+                        code0, ph0 = int(sc_np[p.tail.start + b]), sp_np[p.tail.start + b]
+                        for g in range(n_seg):
+                            codes, phases, _ = self._tail_numpy_segment(ta_np[b, g], tt_np[b, g], code0, ph0)
+                            codes_h[b, g] = codes
+                            code0, ph0 = int(codes[-1]), phases[-1]
             return codes_h
         aud_q, txt_q = np.asarray(aud_q), np.asarray(txt_q)
         ta, tt = self.match_tables(aud_q.reshape((Q,) + aud_q.shape[3:]), txt_q.reshape(Q, -1))
@@ -640,7 +713,7 @@ def predict_code_from_audio(train_mfcc, train_code, test_mfcc, data_stats, train
     return np.array(motion_output)
 
 
-def build_knn_from_files(a, mode="A", tail="device", device=None, seq_range=None, process_group=None):
+def build_knn_from_files(a, mode="A", tail="auto", device=None, seq_range=None, process_group=None):
     """Lean construction used by the CLI and the bench: reads the 8 npz files and
     uploads only what the shipped matcher scans."""
     from .data_processing import load_match_inputs
@@ -659,7 +732,7 @@ def build_knn_from_files(a, mode="A", tail="device", device=None, seq_range=None
 def main_codebook(maxFrames=0, mode=None, tail=None):
     """GestureKNN.py:816-845: load, match every test segment, write knn_pred."""
     mode = mode or getattr(args, "mode", "A")
-    tail = tail or getattr(args, "tail", "device")
+    tail = tail or getattr(args, "tail", "auto")
     device = torch.device("cuda", getattr(args, "gpu", 0))
     knn, inp = build_knn_from_files(args, mode=mode, tail=tail, device=device)
     n_test_seq = maxFrames if maxFrames != 0 else inp["n_test"]                            # :740

@@ -35,6 +35,11 @@ class ConvTcDesc(C.Structure):
     ]
 
 
+class SlicedSeg(C.Structure):
+    _fields_ = [("db_slices", C.c_void_p), ("q_slices", C.c_void_p), ("sacc", C.c_void_p), ("n_kblocks", C.c_int32),
+                ("pad", C.c_int32)]
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _INT = C.c_int
@@ -53,11 +58,22 @@ SIGNATURES = {
     "qpg_cand_cosine_minbycode": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _P]),
     "qpg_cand_cosine_minbycode_team": (_INT, [_P, _P, _P, _I64, _INT, _I64, _P, _INT, _P, _INT, _INT, _P]),
     "qpg_cand_cosine2_minbycode": (_INT, [_P, _P, _P, _P, _I64, _INT, _INT, _I64, _P, _INT, _P, _P, _P]),
+    "qpg_sliced_bytes": (C.c_size_t, [_I64, _INT]),
+    "qpg_sliced_query_bytes": (C.c_size_t, [_INT, _INT]),
+    "qpg_slice_rows_i8": (_INT, [_P, _I64, _INT, _P, _P, _P, _P, _P, _P]),
+    "qpg_slice_queries_i8": (_INT, [_P, _INT, _INT, _I64, _P, _INT, _P, _P, _P]),
+    "qpg_sliced_scan_i8": (_INT, [_P, _INT, _I64, _INT, _INT, _P]),
+    "qpg_sliced_scan_ref": (_INT, [_P, _P, _INT, _I64, _INT, _INT, _INT, _P, _P]),
+    "qpg_sliced_bins": (_INT, [_P, _I64, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _INT, _P, _I64, _P, _P, _P]),
+    "qpg_sliced_resolve": (_INT, [_P, _INT, _I64, _INT, _P, _INT, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "qpg_match_lookup": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
+    "qpg_match_walk": (_INT, [_P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
     "qpg_l2_prefetch": (_INT, [_P, C.c_size_t, _P]),
     "qpg_table_merge": (_INT, [_P, _INT, _I64, _P, _P]),
     "qpg_rank512": (_INT, [_P, _INT, _P, _P]),
+    "qpg_rank512_ties": (_INT, [_P, _INT, _P, _P, _P]),
     "qpg_match_tail": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
     "qpg_match_tail_segments": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _INT, _INT, _P,
                                        _P, _P, _P, _P, _P]),

@@ -51,10 +51,10 @@ __device__ __forceinline__ double f32_to_f64_alu(float f) {
 __device__ __forceinline__ double cosine_distance(double dot, double sqq, double sqx) {
   // sklearn: normalize() leaves an all-zero vector at zero (norm 0 -> 1), then
   // 0.5*||a-b||^2 = 0.5*(|a|^2+|b|^2) - <a,b> with |a|,|b| in {0,1}.
-  const double a = sqq > 0.0 ? 1.0 : 0.0;
-  const double b = sqx > 0.0 ? 1.0 : 0.0;
+  const double a = sqq > kTinySq ? 1.0 : 0.0;
+  const double b = sqx > kTinySq ? 1.0 : 0.0;
   double c = 0.0;
-  if (sqq > 0.0 && sqx > 0.0) c = dot / (sqrt(sqq) * sqrt(sqx));
+  if (sqq > kTinySq && sqx > kTinySq) c = dot / (sqrt(sqq) * sqrt(sqx));
   double d = 0.5 * (a + b) - c;
   return d < 0.0 ? 0.0 : d;
 }

@@ -27,19 +27,32 @@ __global__ void table_merge_kernel(const Pair* __restrict__ parts, int n_parts, 
 }
 
 // ranks[q][c] = #{c' : d[c'] < d[c] or (d[c'] == d[c] and c' < c)}
-__global__ void __launch_bounds__(KB) rank512_kernel(const Pair* __restrict__ table, int32_t* __restrict__ ranks) {
+// qflags[q] (optional) = 1 when two NON-EMPTY bins hold exactly the same distance (the reference's rank of those
+// bins is whatever NumPy's unstable argsort does with ties)
+__global__ void __launch_bounds__(KB) rank512_kernel(const Pair* __restrict__ table, int32_t* __restrict__ ranks,
+                                                     int32_t* __restrict__ qflags) {
   __shared__ unsigned long long d[KB];
+  __shared__ int s_tie;
   const int q = blockIdx.x, c = threadIdx.x;
-  const unsigned long long mine = table[(size_t)q * KB + c].d;
+  const Pair e = table[(size_t)q * KB + c];
+  const unsigned long long mine = e.d;
+  const bool nonempty = (long long)e.id >= 0;
   d[c] = mine;
+  if (c == 0) s_tie = 0;
   __syncthreads();
-  int r = 0;
+  int r = 0, tie = 0;
 #pragma unroll 8
   for (int j = 0; j < KB; ++j) {
     const unsigned long long o = d[j];
     r += (o < mine) || (o == mine && j < c);
+    tie |= (o == mine && j != c);
   }
   ranks[(size_t)q * KB + c] = r;
+  if (qflags) {
+    if (tie && nonempty) s_tie = 1;
+    __syncthreads();
+    if (c == 0) qflags[q] = s_tie;
+  }
 }
 
 // pull a buffer into L2 (prefetch.global.L2 per 128-byte line): the streaming scans evict the small tables the
@@ -291,7 +304,16 @@ extern "C" int qpg_rank512(const qpg_pair_t* table, int Q, int32_t* ranks, void*
   QPG_CHECK_ARG(Q >= 0, "Q >= 0");
   if (Q == 0) return QPG_OK;
   QPG_CHECK_ARG(table && ranks, "null pointer");
-  rank512_kernel<<<Q, KB, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Pair*>(table), ranks);
+  rank512_kernel<<<Q, KB, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Pair*>(table), ranks, nullptr);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_rank512_ties(const qpg_pair_t* table, int Q, int32_t* ranks, int32_t* qflags, void* stream) {
+  QPG_CHECK_ARG(Q >= 0, "Q >= 0");
+  if (Q == 0) return QPG_OK;
+  QPG_CHECK_ARG(table && ranks && qflags, "null pointer");
+  rank512_kernel<<<Q, KB, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Pair*>(table), ranks, qflags);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

@@ -44,6 +44,9 @@ void count_launch(int n = 1);
 int sm_count();
 
 constexpr double kEmptyDist = 1e3;  // GestureKNN.py:668,709
+// sklearn's normalize() (called by paired_cosine_distances) leaves a row unscaled when its norm is below
+// 10 * eps(float64): such a row counts as all-zero.  Squared threshold.
+constexpr double kTinySq = 4.930380657631324e-30;
 
 // ---- (distance, id) pairs ordered lexicographically ---------------------------
 // Distances are non-negative doubles, so their bit patterns order like

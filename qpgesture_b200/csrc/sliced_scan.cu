@@ -1,0 +1,813 @@
+// One-pass candidate scan for up to 64 query steps: exact integer dot products on the tensor cores
+// (tcgen05.mma kind::i8, int32 accumulators in TMEM) over an int8-"sliced" copy of the window table,
+// plus the interval logic that turns them into the exact (distance, window id) tables of
+// CodeKNN.search_audio_cands / search_text_cands (GestureKNN.py:666-691, :708-721).
+//
+// Why: one query step is 0.5 flop/B (HBM bound), but a 24-s clip is 48 steps that all read the same
+// table.  48 steps per pass are 24 flop/B - past the FFMA and far past the FP64 ridge - so the only way
+// to stay on the HBM roofline with ONE pass per clip is the tensor pipe.  Floating-point tensor-core
+// accumulation has no documented rounding, so the table is stored as integers instead:
+//
+//   x' = x * 2^-colexp[k]                       (optional per-column power of two, exact)
+//   X  = rint(x' * 2^(30-ex)),  |x'| < 2^ex     (31-bit fixed point relative to the row maximum)
+//   X  = d0*2^24 + d1*2^16 + d2*2^8 + d3        (balanced base-256 digits = four int8 slices)
+//
+// and the queries likewise (Y, digits e_t).  The kernel accumulates the ten digit products with
+// s+t <= 3, P_j = sum_{s+t=j} sum_k d_s[k] e_t[k], EXACTLY (integers), so
+//   dot(x,q) = 2^(ex+eq-36) * v + R,   v = P0*2^24 + P1*2^16 + P2*2^8 + P3  (int64),
+//   |R| <= 2^(ex+eq-60) * (L1(X)/2 + L1(Y)/2 + K/4 + 128*65793*sum_k(|e1|+|e2|+|e3|))
+// (quantisation |dX|,|dY| <= 1/2 plus the six dropped products, |d_s| <= 128).  That is a cosine error
+// of ~1e-7 on Gaussian data with a rigorous, per-(row,query) bound: every distance is an interval
+// [lo, hi], a bin's winner is decided when only one interval can hold the minimum, the rank transform is
+// decided when bin intervals do not overlap, and the few undecided (query, bin) pairs (~0.15 %) are
+// re-evaluated in float64 from the float32 table (`exact_distance`, same arithmetic as cand_cosine.cu).
+// Integer partial sums are associative, so the stream-K split over CTAs with 64-bit global atomics is
+// bit-reproducible.
+//
+// Layouts (all tiles are pre-swizzled images of what the UMMA descriptor expects: K-major, 128-byte rows,
+// SWIZZLE_128B, 8-row groups 1024 bytes apart - one plain cp.async.bulk per tile, no tensor map):
+//   database slices  [RT = ceil(W/128)][NKB = ceil(D/128)][4 slices][128 rows x 128 B]   (rows in bin order)
+//   query slices     [NKB][4 slices][n_pad rows x 128 B],  n_pad in {16,32,48,64}
+//   sacc             int64 [n_pad][Wpad]   v per (query, sorted row position)
+#include "qpg_common.cuh"
+
+namespace qpg {
+namespace {
+
+constexpr int NS = 4;                 // int8 slices per value
+constexpr int TM = 128;               // rows per tile (UMMA M, TMEM lanes)
+constexpr int KBW = 128;              // columns (bytes) per k-block = one swizzle row
+constexpr int SLICE_BYTES = TM * KBW; // 16 KiB
+constexpr int STAGES = 2;
+constexpr int MAX_NPAD = 64;
+constexpr int KB = QPG_CODEBOOK_SIZE;
+constexpr double DROP_C = 128.0 * 65793.0;   // bound of the dropped digit products per unit of sum(|e1|+|e2|+|e3|)
+constexpr double EPS_SLACK = 1e-12;          // float64 rounding of both evaluations (<= 5e-13 at D = 6144)
+
+// byte offset of element (row r, column byte kbyte) inside a [rows x 128 B] SWIZZLE_128B tile
+__host__ __device__ __forceinline__ uint32_t swz_offset(uint32_t r, uint32_t kbyte) {
+  return (r >> 3) * 1024u + (r & 7u) * 128u + ((((kbyte >> 4) ^ (r & 7u)) & 7u) << 4) + (kbyte & 15u);
+}
+
+// ------------------------------------------------------------------ slicing (database rows and queries)
+struct RowInfo {   // per sorted database row
+  double r1;       // 2^(ex-60) / |x|        (0 for an all-zero row)
+  double r2;       // 0.5 * L1(X) * r1
+};
+
+// One CTA per output row `pos`.  DB mode (n_rows_tile = 128): tile (pos/128, kb, s); query mode: one tile
+// column of n_pad rows, row = pos.  sign = -1 applies 2^-colexp (database), +1 applies 2^+colexp (queries).
+template <bool kQuery>
+__global__ void __launch_bounds__(128)
+    slice_kernel(const float* __restrict__ rows, int64_t n_rows, int D, int64_t ld, const int32_t* __restrict__ order,
+                 const int8_t* __restrict__ col_exp, int nkb, int n_pad, int8_t* __restrict__ out,
+                 const double* __restrict__ sqnorm_in, RowInfo* __restrict__ row_info,
+                 qpg_qinfo_t* __restrict__ q_info) {
+  __shared__ double s_red[4];
+  __shared__ unsigned long long s_l1[4], s_el[4];
+  __shared__ int s_ex;
+  const int64_t pos = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t src = order ? (int64_t)order[pos] : pos;
+  const float* x = rows + src * ld;
+  const int Dp = nkb * KBW;
+
+  // pass 1: maximum magnitude (after the column scaling) and, for queries, the squared norm
+  double mx = 0.0, sq = 0.0;
+  for (int k = tid; k < D; k += 128) {
+    double v = (double)x[k];
+    sq = fma(v, v, sq);
+    if (col_exp) v = scalbn(v, kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
+    mx = fmax(mx, fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) s_red[warp] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    const double m = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
+    s_ex = m > 0.0 ? ilogb(m) + 1 : 0;         // |x'| < 2^ex
+  }
+  __syncthreads();
+  const int ex = s_ex;
+  if (kQuery) {   // squared norm in a fixed order (lane-strided partials, shuffle tree, 4 warps in order)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) s_red[warp] = sq;           // s_red reuse is safe: everyone passed the barrier above
+  }
+
+  // pass 2: digits.  Thread t owns columns 4t..4t+3 of every 512-column stripe -> one 32-bit store per slice
+  unsigned long long l1 = 0, el = 0;
+  const int64_t tile_row = kQuery ? pos : (pos % TM);
+  const int64_t rt = kQuery ? 0 : pos / TM;
+  for (int k0 = 4 * tid; k0 < Dp; k0 += 512) {
+    uint32_t w[NS] = {0u, 0u, 0u, 0u};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = k0 + i;
+      long long X = 0;
+      if (k < D) {
+        double v = (double)x[k];
+        if (col_exp) v = scalbn(v, kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
+        X = llrint(scalbn(v, 30 - ex));
+      }
+      l1 += (unsigned long long)(X < 0 ? -X : X);
+      long long r = X;
+      int dig[NS];
+#pragma unroll
+      for (int s = NS - 1; s >= 1; --s) {
+        const long long d = ((r + 128) & 255) - 128;
+        dig[s] = (int)d;
+        r = (r - d) >> 8;
+        el += (unsigned long long)(d < 0 ? -d : d);
+      }
+      dig[0] = (int)r;                           // |r| <= 64 because |X| <= 2^30
+#pragma unroll
+      for (int s = 0; s < NS; ++s) w[s] |= ((uint32_t)dig[s] & 0xffu) << (8 * i);
+    }
+    const int kb = k0 / KBW, kbyte = k0 % KBW;
+    const size_t tile_bytes = kQuery ? (size_t)n_pad * KBW : (size_t)SLICE_BYTES;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) {
+      const size_t base = (((size_t)rt * nkb + kb) * NS + s) * tile_bytes;
+      *reinterpret_cast<uint32_t*>(out + base + swz_offset((uint32_t)tile_row, (uint32_t)kbyte)) = w[s];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) {
+    l1 += __shfl_xor_sync(0xffffffffu, l1, o);
+    el += __shfl_xor_sync(0xffffffffu, el, o);
+  }
+  if (lane == 0) {
+    s_l1[warp] = l1;
+    s_el[warp] = el;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    const double L1 = (double)(s_l1[0] + s_l1[1] + s_l1[2] + s_l1[3]);
+    const double EL = (double)(s_el[0] + s_el[1] + s_el[2] + s_el[3]);
+    if (kQuery) {
+      const double sqq = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
+      qpg_qinfo_t qi;
+      qi.sq = sqq;
+      qi.g = sqq > kTinySq ? scalbn(1.0, ex) / sqrt(sqq) : 0.0;
+      qi.h = 0.5 * L1 + DROP_C * EL + 0.25 * (double)D;
+      qi.ex = ex;
+      qi.pad = 0;
+      q_info[pos] = qi;
+    } else {
+      const double sqx = sqnorm_in[src];
+      RowInfo ri;
+      ri.r1 = sqx > kTinySq ? scalbn(1.0, ex - 60) / sqrt(sqx) : 0.0;
+      ri.r2 = 0.5 * L1 * ri.r1;
+      row_info[pos] = ri;
+    }
+  }
+}
+
+// ------------------------------------------------------------------ tcgen05 / TMEM wrappers
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma_i8(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major SWIZZLE_128B operand tile with 128-byte rows (same descriptor as conv1d_tc.cu, proven on B200)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void red_add_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+struct SegParam {
+  const int8_t* A;            // database slices of this feature block
+  const int8_t* B;            // query slices
+  unsigned long long* sacc;   // [n_pad][Wpad]
+  int nkb;
+};
+struct ScanParams {
+  SegParam seg[2];
+  int nseg, nkb_total, n_pad, nq;
+  long long RT, W, Wpad, total_units;
+};
+
+// a "run" = consecutive units of one (row tile, feature block): one TMEM accumulator stage
+struct UnitPos {
+  long long rt;
+  int seg, kb;
+};
+__device__ __forceinline__ UnitPos unit_pos(const ScanParams& p, long long u) {
+  UnitPos r;
+  r.rt = u / p.nkb_total;
+  const int kbu = (int)(u - r.rt * p.nkb_total);
+  r.seg = kbu < p.seg[0].nkb ? 0 : 1;
+  r.kb = r.seg == 0 ? kbu : kbu - p.seg[0].nkb;
+  return r;
+}
+
+__global__ void __launch_bounds__(256, 1) sliced_scan_kernel(const ScanParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  const uint32_t b_slice_bytes = (uint32_t)p.n_pad * KBW;
+  const uint32_t stage_bytes = NS * SLICE_BYTES + NS * MAX_NPAD * KBW;      // fixed stride, 96 KiB
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
+  uint64_t* empty = full + STAGES;
+  uint64_t* acc_full = empty + STAGES;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long u0 = (long long)blockIdx.x * p.total_units / gridDim.x;
+  const long long u1 = (long long)(blockIdx.x + 1) * p.total_units / gridDim.x;
+
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);       // one arrive per epilogue warp
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer: one bulk copy per slice tile, query slices in one copy =====
+    if (lane == 0) {
+      int it = 0;
+      for (long long u = u0; u < u1; ++u, ++it) {
+        const UnitPos up = unit_pos(p, u);
+        const int8_t* seg_a = up.seg == 0 ? p.seg[0].A : p.seg[1].A;
+        const int8_t* seg_b = up.seg == 0 ? p.seg[0].B : p.seg[1].B;
+        const int seg_nkb = up.seg == 0 ? p.seg[0].nkb : p.seg[1].nkb;
+        const int s = it % STAGES;
+        if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+        unsigned char* st = smem + (size_t)s * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], NS * SLICE_BYTES + NS * b_slice_bytes);
+        const int8_t* a = seg_a + ((size_t)up.rt * seg_nkb + up.kb) * (size_t)(NS * SLICE_BYTES);
+#pragma unroll
+        for (int sl = 0; sl < NS; ++sl)
+          bulk_g2s(st + sl * SLICE_BYTES, a + (size_t)sl * SLICE_BYTES, SLICE_BYTES, &full[s]);
+        bulk_g2s(st + NS * SLICE_BYTES, seg_b + (size_t)up.kb * NS * b_slice_bytes, NS * b_slice_bytes, &full[s]);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer: 4 k-steps x 10 digit products per unit =====
+    if (lane == 0) {
+      // D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
+                             ((uint32_t)(TM >> 4) << 24);
+      int it = 0, run = 0;
+      bool first = true;
+      for (long long u = u0; u < u1; ++u, ++it) {
+        const UnitPos up = unit_pos(p, u);
+        const int as = run & 1;
+        if (first && run >= 2) {
+          mbar_wait(&acc_empty[as], ((run >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const int s = it % STAGES;
+        mbar_wait(&full[s], (it / STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
+        const uint32_t b_addr = a_addr + NS * SLICE_BYTES;
+        const uint32_t acc0 = tmem_base + (uint32_t)(as * NS * p.n_pad);
+#pragma unroll
+        for (int k4 = 0; k4 < KBW / 32; ++k4) {
+#pragma unroll
+          for (int j = 0; j < NS; ++j) {
+#pragma unroll
+            for (int sa = 0; sa <= j; ++sa) {
+              const int tb = j - sa;
+              const uint64_t a_desc = umma_desc_sw128(a_addr + sa * SLICE_BYTES) + 2u * k4;
+              const uint64_t b_desc = umma_desc_sw128(b_addr + tb * b_slice_bytes) + 2u * k4;
+              tc_mma_i8(acc0 + (uint32_t)(j * p.n_pad), a_desc, b_desc, idesc, (first && k4 == 0 && sa == 0) ? 0u : 1u);
+            }
+          }
+        }
+        tc_commit(&empty[s]);
+        first = false;
+        bool run_ends = (u + 1 == u1);
+        if (!run_ends) {
+          const UnitPos nx = unit_pos(p, u + 1);
+          run_ends = nx.rt != up.rt || nx.seg != up.seg;
+        }
+        if (run_ends) {
+          tc_commit(&acc_full[as]);
+          ++run;
+          first = true;
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ===== epilogue: TMEM -> int64 v -> global accumulate =====
+    const int quarter = warp & 3;
+    int run = 0;
+    long long u = u0;
+    while (u < u1) {
+      const UnitPos up = unit_pos(p, u);
+      // extent of this run inside [u0, u1)
+      const long long seg_first = up.rt * p.nkb_total + (up.seg == 0 ? 0 : p.seg[0].nkb);
+      const long long seg_end = seg_first + (up.seg == 0 ? p.seg[0].nkb : p.seg[1].nkb);
+      const long long run_end = seg_end < u1 ? seg_end : u1;
+      const bool whole = (u == seg_first) && (run_end == seg_end);     // this CTA owns the full K range
+      const int as = run & 1;
+      mbar_wait(&acc_full[as], (run >> 1) & 1);
+      tc_fence_after();
+      const long long row = up.rt * TM + quarter * 32 + lane;
+      unsigned long long* dst = (up.seg == 0 ? p.seg[0].sacc : p.seg[1].sacc) + row;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * NS * p.n_pad);
+      for (int qc = 0; qc < p.n_pad; qc += 16) {
+        uint32_t a0[16], a1[16], a2[16], a3[16];
+        tmem_ld_x16(tbase + (uint32_t)(0 * p.n_pad + qc), a0);
+        tmem_ld_x16(tbase + (uint32_t)(1 * p.n_pad + qc), a1);
+        tmem_ld_x16(tbase + (uint32_t)(2 * p.n_pad + qc), a2);
+        tmem_ld_x16(tbase + (uint32_t)(3 * p.n_pad + qc), a3);
+        tmem_ld_wait();
+        if (row < p.W) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            if (qc + i < p.nq) {
+              const long long v = ((((long long)(int)a0[i] * 256 + (long long)(int)a1[i]) * 256 + (long long)(int)a2[i]) * 256) +
+                                  (long long)(int)a3[i];
+              unsigned long long* d = dst + (size_t)(qc + i) * p.Wpad;
+              if (whole) *d = (unsigned long long)v;
+              else red_add_u64(d, (unsigned long long)v);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[as]);
+      ++run;
+      u = run_end;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// Plain CUDA-core evaluation of the same integer sums from the same tile images (test / debug only):
+// validates the tile layout and the tensor-core kernel independently of each other.
+__global__ void sliced_scan_ref_kernel(const int8_t* __restrict__ A, const int8_t* __restrict__ B, int nkb, int n_pad,
+                                       int nq, int q_stride, long long W, long long Wpad,
+                                       long long* __restrict__ sacc) {
+  const long long row = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int q = blockIdx.y * q_stride;
+  if (row >= W || q >= nq) return;
+  const long long rt = row / TM;
+  const uint32_t r = (uint32_t)(row % TM);
+  long long P[NS] = {0, 0, 0, 0};
+  for (int kb = 0; kb < nkb; ++kb) {
+    for (int kbyte = 0; kbyte < KBW; ++kbyte) {
+      int d[NS], e[NS];
+#pragma unroll
+      for (int s = 0; s < NS; ++s) {
+        d[s] = A[(((size_t)rt * nkb + kb) * NS + s) * SLICE_BYTES + swz_offset(r, kbyte)];
+        e[s] = B[((size_t)kb * NS + s) * (size_t)n_pad * KBW + swz_offset((uint32_t)q, kbyte)];
+      }
+#pragma unroll
+      for (int j = 0; j < NS; ++j)
+#pragma unroll
+        for (int sa = 0; sa <= j; ++sa) P[j] += (long long)(d[sa] * e[j - sa]);
+    }
+  }
+  sacc[(size_t)q * Wpad + row] = ((P[0] * 256 + P[1]) * 256 + P[2]) * 256 + P[3];
+}
+
+// ------------------------------------------------------------------ exact float64 re-evaluation
+// distance of query `q` (float32 [D], squared norm sqq) to row w of a float32 table in the 4 KiB tile
+// layout of qpg_pack_rows_f32; warp-cooperative, fixed summation order, result on every lane.
+__device__ __forceinline__ double exact_distance(const float* __restrict__ packed, int NC, int64_t w,
+                                                 const float* __restrict__ q, int D, double sqq, double sqx, int lane) {
+  const float* base = packed + (((size_t)(w >> 3) * NC) * 8 + (w & 7)) * 128;
+  double acc = 0.0;
+  for (int c = 0; c < NC; ++c) {
+    const float4 xv = *reinterpret_cast<const float4*>(base + (size_t)c * 1024 + 4 * lane);
+    const int k = c * 128 + 4 * lane;
+    float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k + 3 < D) qv = *reinterpret_cast<const float4*>(q + k);
+    else {
+      if (k < D) qv.x = q[k];
+      if (k + 1 < D) qv.y = q[k + 1];
+      if (k + 2 < D) qv.z = q[k + 2];
+    }
+    acc = fma((double)xv.x, (double)qv.x, acc);
+    acc = fma((double)xv.y, (double)qv.y, acc);
+    acc = fma((double)xv.z, (double)qv.z, acc);
+    acc = fma((double)xv.w, (double)qv.w, acc);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const double a = sqq > kTinySq ? 1.0 : 0.0, b = sqx > kTinySq ? 1.0 : 0.0;
+  double c = 0.0;
+  if (sqq > kTinySq && sqx > kTinySq) c = acc / (sqrt(sqq) * sqrt(sqx));
+  const double d = 0.5 * (a + b) - c;
+  return d < 0.0 ? 0.0 : d;
+}
+
+struct Interval {
+  double lo, hi;
+};
+// distance interval of (query, sorted row) from the exact integer v
+__device__ __forceinline__ Interval filter_interval(long long v, const RowInfo ri, const qpg_qinfo_t& qi) {
+  const double a = qi.g > 0.0 ? 1.0 : 0.0, b = ri.r1 > 0.0 ? 1.0 : 0.0;
+  const double c = (double)v * (ri.r1 * 16777216.0) * qi.g;                 // 2^(ex+eq-36) v / (|x||q|)
+  const double eps = (qi.g * fma(ri.r1, qi.h, ri.r2)) * (1.0 + 1e-9) + EPS_SLACK;
+  const double d = 0.5 * (a + b) - c;
+  Interval iv;
+  iv.lo = d - eps;
+  iv.hi = d + eps;
+  if (iv.lo < 0.0) iv.lo = 0.0;
+  if (iv.hi < 0.0) iv.hi = 0.0;
+  return iv;
+}
+
+// ------------------------------------------------------------------ per-bin records
+// One warp per (query, start code): U = min hi over the bin's rows; candidates = rows whose interval reaches
+// below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly those rows
+// (lexicographic (d, id) minimum) -> exact record lo = hi = d.
+__global__ void __launch_bounds__(256)
+    sliced_bins_kernel(const long long* __restrict__ sacc, long long Wpad, int nq, const int32_t* __restrict__ bin_start,
+                       const RowInfo* __restrict__ row_info, const int32_t* __restrict__ order,
+                       const double* __restrict__ sqnorm, int64_t id_offset, int64_t row_base,
+                       const qpg_qinfo_t* __restrict__ q_info, const float* __restrict__ packed, int NC, int D,
+                       const float* __restrict__ q, int64_t ldq, qpg_bin_t* __restrict__ out,
+                       unsigned long long* __restrict__ stats) {
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= (long long)nq * KB) return;
+  const int qi_ = (int)(wid / KB), c = (int)(wid % KB);
+  const qpg_qinfo_t qi = q_info[qi_];
+  const int b0 = bin_start[c], b1 = bin_start[c + 1];
+  const long long* sv = sacc + (size_t)qi_ * Wpad;
+  qpg_bin_t rec;
+  rec.lo = kEmptyDist;
+  rec.hi = kEmptyDist;
+  rec.id = -1;
+  rec.n = 0;
+  rec.flags = 0;
+  if (b1 > b0) {
+    double U = 1e300;
+    for (int pos = b0 + lane; pos < b1; pos += 32) {
+      const Interval iv = filter_interval(sv[pos], row_info[pos], qi);
+      U = fmin(U, iv.hi);
+    }
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) U = fmin(U, __shfl_xor_sync(0xffffffffu, U, o));
+    int n = 0;
+    double best_lo = 1e300, best_d = 1e300;
+    long long best_id = -1, single_pos = -1;
+    for (int base = b0; base < b1; base += 32) {
+      const int pos = base + lane;
+      bool cand = false;
+      Interval iv{0.0, 0.0};
+      if (pos < b1) {
+        iv = filter_interval(sv[pos], row_info[pos], qi);
+        cand = iv.lo <= U;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, cand);
+      const int cnt = __popc(m);
+      if (cnt == 0) continue;
+      if (n == 0 && cnt == 1) {            // remember the first lone candidate; verified later only if another shows up
+        const int src_lane = __ffs(m) - 1;
+        single_pos = base + src_lane;
+        best_lo = __shfl_sync(0xffffffffu, iv.lo, src_lane);
+        n = 1;
+        continue;
+      }
+      // more than one candidate so far: evaluate exactly (including the remembered one)
+      if (n == 1 && single_pos >= 0) {
+        const long long w = order[single_pos];
+        const double d = exact_distance(packed, NC, w + row_base, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w + row_base], lane);
+        best_d = d;
+        best_id = id_offset + w;
+        single_pos = -1;
+      }
+      unsigned mm = m;
+      while (mm) {
+        const int src_lane = __ffs(mm) - 1;
+        mm &= mm - 1;
+        const long long w = order[base + src_lane];
+        const double d = exact_distance(packed, NC, w + row_base, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w + row_base], lane);
+        const long long id = id_offset + w;
+        if (d < best_d || (d == best_d && id < best_id)) {
+          best_d = d;
+          best_id = id;
+        }
+      }
+      n += cnt;
+    }
+    if (n == 1 && single_pos >= 0) {
+      rec.lo = best_lo;
+      rec.hi = U;
+      rec.id = id_offset + order[single_pos];
+      rec.n = 1;
+    } else {
+      rec.lo = best_d;
+      rec.hi = best_d;
+      rec.id = best_id;
+      rec.n = 1;
+      rec.flags = 1;                         // exact
+      if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
+    }
+  } else {
+    rec.flags = 1;                           // empty bins are exact (sentinel)
+  }
+  if (lane == 0) out[(size_t)qi_ * KB + c] = rec;
+}
+
+// ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
+// One CTA (512 threads, thread = start code) per query.  parts [P][nq][512] (P = 1 on a single GPU, the
+// all-gathered per-rank records when database rows are sharded).  `packed`/`sqnorm` address rows by GLOBAL
+// window id - first_id (a replicated float32 copy of the whole table), so any rank can re-evaluate any
+// candidate.  Output: table [nq][512] (distance exact where it had to be decided, else the filter value),
+// ranks [nq][512] (stable, as qpg_rank512), qflags [nq] bit0 = exact tie between two non-empty bins.
+__global__ void __launch_bounds__(KB)
+    sliced_resolve_kernel(const qpg_bin_t* __restrict__ parts, int P, long long part_stride, const float* __restrict__ packed, int NC,
+                          int D, const double* __restrict__ sqnorm, int64_t first_id,
+                          const qpg_qinfo_t* __restrict__ q_info, const float* __restrict__ q, int64_t ldq,
+                          Pair* __restrict__ table, int32_t* __restrict__ ranks, int32_t* __restrict__ qflags,
+                          unsigned long long* __restrict__ stats) {
+  __shared__ double s_lo[KB], s_hi[KB];
+  __shared__ unsigned long long s_d[KB];
+  __shared__ long long s_id[KB];
+  __shared__ int s_list[KB];
+  __shared__ int s_n, s_tie;
+  const int qi_ = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  if (c == 0) {
+    s_n = 0;
+    s_tie = 0;
+  }
+  // merge: U* = min hi; candidates = parts with lo <= U*
+  double U = 1e300;
+  for (int p = 0; p < P; ++p) {
+    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + c];
+    if (r.id >= 0) U = fmin(U, r.hi);
+  }
+  int ncand = 0;
+  double lo = kEmptyDist, hi = kEmptyDist;
+  long long id = -1;
+  bool exact = true;
+  for (int p = 0; p < P; ++p) {
+    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + c];
+    if (r.id >= 0 && r.lo <= U) {
+      if (ncand == 0) {
+        lo = r.lo;
+        id = r.id;
+        exact = (r.flags & 1) != 0;
+      } else {
+        if (r.lo < lo) lo = r.lo;
+        exact = false;
+      }
+      ++ncand;
+    }
+  }
+  if (ncand > 0) hi = U;
+  if (ncand == 1 && exact) lo = hi;             // an exact record is a point (hi == lo already)
+  s_lo[c] = lo;
+  s_hi[c] = hi;
+  __syncthreads();
+  bool need = ncand > 1;
+  if (ncand >= 1 && !need && !(exact && lo == hi)) {
+    for (int j = 0; j < KB; ++j) {
+      if (j != c && s_lo[j] <= hi && lo <= s_hi[j] && s_hi[j] < kEmptyDist) {
+        need = true;
+        break;
+      }
+    }
+  } else if (ncand == 1 && exact) {
+    // a point still needs nothing; intervals that contain it are flagged by their own thread
+  }
+  if (need) s_list[atomicAdd(&s_n, 1)] = c;
+  __syncthreads();
+  const int n_list = s_n;
+  s_id[c] = id;
+  s_d[c] = (unsigned long long)__double_as_longlong(ncand >= 1 ? 0.5 * (lo + hi) : kEmptyDist);
+  __syncthreads();
+  const qpg_qinfo_t qi = q_info[qi_];
+  for (int it = warp; it < n_list; it += KB / 32) {
+    const int cc = s_list[it];
+    double Uc = s_hi[cc];
+    double bd = 1e300;
+    long long bid = -1;
+    for (int p = 0; p < P; ++p) {
+      const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + cc];
+      if (r.id >= 0 && r.lo <= Uc) {
+        double d;
+        if (r.flags & 1) d = r.lo;
+        else {
+          const int64_t w = r.id - first_id;
+          d = exact_distance(packed, NC, w, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w], lane);
+        }
+        if (d < bd || (d == bd && r.id < bid)) {
+          bd = d;
+          bid = r.id;
+        }
+      }
+    }
+    if (lane == 0) {
+      s_d[cc] = (unsigned long long)__double_as_longlong(bd);
+      s_id[cc] = bid;
+    }
+  }
+  __syncthreads();
+  if (c == 0 && stats) atomicAdd(&stats[1], (unsigned long long)n_list);
+  // stable rank (ties -> lower code first) + tie flag among non-empty bins
+  const unsigned long long mine = s_d[c];
+  const unsigned long long empty_bits = (unsigned long long)__double_as_longlong(kEmptyDist);
+  int r = 0, tie = 0;
+#pragma unroll 8
+  for (int j = 0; j < KB; ++j) {
+    const unsigned long long o = s_d[j];
+    r += (o < mine) || (o == mine && j < c);
+    tie |= (o == mine && j != c && mine != empty_bits);
+  }
+  if (tie) s_tie = 1;
+  Pair out;
+  out.d = mine;
+  out.id = (unsigned long long)s_id[c];
+  table[(size_t)qi_ * KB + c] = out;
+  ranks[(size_t)qi_ * KB + c] = r;
+  __syncthreads();
+  if (c == 0 && qflags) qflags[qi_] = s_tie;
+}
+
+}  // namespace
+}  // namespace qpg
+
+using namespace qpg;
+
+extern "C" size_t qpg_sliced_bytes(int64_t n_rows, int D) {
+  if (n_rows <= 0 || D <= 0) return 0;
+  const size_t rt = (size_t)((n_rows + TM - 1) / TM), nkb = (size_t)((D + KBW - 1) / KBW);
+  return rt * nkb * NS * SLICE_BYTES;
+}
+
+extern "C" size_t qpg_sliced_query_bytes(int D, int n_pad) {
+  if (D <= 0 || n_pad <= 0) return 0;
+  return (size_t)((D + KBW - 1) / KBW) * NS * (size_t)n_pad * KBW;
+}
+
+extern "C" int qpg_slice_rows_i8(const float* rows, int64_t W, int D, const int32_t* order, const int8_t* col_exp,
+                                 const double* row_sqnorm, int8_t* slices, void* row_info, void* stream) {
+  QPG_CHECK_ARG(W >= 0 && D > 0 && D <= 32768, "W >= 0, 0 < D <= 32768 (int32 accumulators)");
+  if (W == 0) return QPG_OK;
+  QPG_CHECK_ARG(rows && row_sqnorm && slices && row_info, "null pointer");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(slices) & 1023) == 0, "slices must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  QPG_CUDA(cudaMemsetAsync(slices, 0, qpg_sliced_bytes(W, D), st));
+  const int nkb = (D + KBW - 1) / KBW;
+  slice_kernel<false><<<(unsigned)W, 128, 0, st>>>(rows, W, D, D, order, col_exp, nkb, 0, slices, row_sqnorm,
+                                                   reinterpret_cast<RowInfo*>(row_info), nullptr);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_slice_queries_i8(const float* q, int Q, int D, int64_t ldq, const int8_t* col_exp, int n_pad,
+                                    int8_t* q_slices, qpg_qinfo_t* q_info, void* stream) {
+  QPG_CHECK_ARG(Q >= 0 && D > 0 && D <= 32768 && ldq >= D, "Q >= 0, 0 < D <= 32768, ldq >= D");
+  QPG_CHECK_ARG(n_pad >= 16 && n_pad <= MAX_NPAD && n_pad % 16 == 0 && Q <= n_pad, "n_pad in {16,32,48,64}, Q <= n_pad");
+  if (Q == 0) return QPG_OK;
+  QPG_CHECK_ARG(q && q_slices && q_info, "null pointer");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(q_slices) & 1023) == 0, "q_slices must be 1024-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Q < n_pad || D % KBW != 0) QPG_CUDA(cudaMemsetAsync(q_slices, 0, qpg_sliced_query_bytes(D, n_pad), st));
+  const int nkb = (D + KBW - 1) / KBW;
+  slice_kernel<true><<<(unsigned)Q, 128, 0, st>>>(q, Q, D, ldq, nullptr, col_exp, nkb, n_pad, q_slices, nullptr, nullptr,
+                                                  q_info);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_sliced_scan_i8(const qpg_sliced_seg_t* segs, int n_segs, int64_t W, int n_pad, int nq,
+                                  void* stream) {
+  QPG_CHECK_ARG(segs && (n_segs == 1 || n_segs == 2), "1 or 2 feature blocks");
+  QPG_CHECK_ARG(W >= 0 && n_pad >= 16 && n_pad <= MAX_NPAD && n_pad % 16 == 0 && nq >= 0 && nq <= n_pad,
+                "n_pad in {16,32,48,64}, nq <= n_pad");
+  if (W == 0 || nq == 0) return QPG_OK;
+  ScanParams p;
+  p.nseg = n_segs;
+  p.nkb_total = 0;
+  for (int i = 0; i < 2; ++i) {
+    p.seg[i].A = nullptr;
+    p.seg[i].B = nullptr;
+    p.seg[i].sacc = nullptr;
+    p.seg[i].nkb = 0;
+  }
+  for (int i = 0; i < n_segs; ++i) {
+    QPG_CHECK_ARG(segs[i].db_slices && segs[i].q_slices && segs[i].sacc && segs[i].n_kblocks > 0, "null block");
+    QPG_CHECK_ARG(segs[i].n_kblocks <= 256, "D <= 32768");
+    QPG_CHECK_ARG(((reinterpret_cast<uintptr_t>(segs[i].db_slices) | reinterpret_cast<uintptr_t>(segs[i].q_slices)) & 127) == 0,
+                  "slices must be 128-byte aligned");
+    p.seg[i].A = segs[i].db_slices;
+    p.seg[i].B = segs[i].q_slices;
+    p.seg[i].sacc = reinterpret_cast<unsigned long long*>(segs[i].sacc);
+    p.seg[i].nkb = segs[i].n_kblocks;
+    p.nkb_total += segs[i].n_kblocks;
+  }
+  p.n_pad = n_pad;
+  p.nq = nq;
+  p.W = W;
+  p.RT = (W + TM - 1) / TM;
+  p.Wpad = p.RT * TM;
+  p.total_units = p.RT * p.nkb_total;
+  int grid = sm_count();
+  if ((long long)grid > p.total_units) grid = (int)p.total_units;
+  const size_t smem = (size_t)STAGES * (NS * SLICE_BYTES + NS * MAX_NPAD * KBW) + 8 * sizeof(uint64_t) + 16;
+  QPG_CUDA(cudaFuncSetAttribute(sliced_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  sliced_scan_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_sliced_scan_ref(const int8_t* db_slices, const int8_t* q_slices, int n_kblocks, int64_t W, int n_pad,
+                                   int nq, int q_stride, int64_t* sacc, void* stream) {
+  QPG_CHECK_ARG(db_slices && q_slices && sacc && n_kblocks > 0 && W > 0 && nq > 0 && nq <= n_pad && q_stride >= 1,
+                "bad argument");
+  const long long Wpad = (W + TM - 1) / TM * TM;
+  dim3 grid((unsigned)((W + 127) / 128), (unsigned)((nq + q_stride - 1) / q_stride));
+  sliced_scan_ref_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(db_slices, q_slices, n_kblocks, n_pad, nq, q_stride, W, Wpad,
+                                                                 reinterpret_cast<long long*>(sacc));
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_sliced_bins(const int64_t* sacc, int64_t W, int nq, const int32_t* bin_start, const void* row_info,
+                               const int32_t* order, const double* row_sqnorm, int64_t id_offset, int64_t row_base,
+                               const qpg_qinfo_t* q_info, const float* packed, int D, const float* q, int64_t ldq,
+                               qpg_bin_t* bins_out, uint64_t* stats, void* stream) {
+  QPG_CHECK_ARG(W >= 0 && nq >= 0 && D > 0 && ldq >= D, "bad size");
+  if (nq == 0) return QPG_OK;
+  QPG_CHECK_ARG(sacc && bin_start && row_info && order && row_sqnorm && q_info && packed && q && bins_out,
+                "null pointer");
+  const long long Wpad = (W + TM - 1) / TM * TM;
+  const long long warps = (long long)nq * KB;
+  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
+  sliced_bins_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const long long*>(sacc), Wpad, nq, bin_start, reinterpret_cast<const RowInfo*>(row_info), order,
+      row_sqnorm, id_offset, row_base, q_info, packed, (D + 127) / 128, D, q, ldq, bins_out,
+      reinterpret_cast<unsigned long long*>(stats));
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_sliced_resolve(const qpg_bin_t* parts, int n_parts, int64_t part_stride, int nq, const float* packed, int D,
+                                  const double* row_sqnorm, int64_t first_id, const qpg_qinfo_t* q_info, const float* q,
+                                  int64_t ldq, qpg_pair_t* table, int32_t* ranks, int32_t* qflags, uint64_t* stats,
+                                  void* stream) {
+  QPG_CHECK_ARG(n_parts >= 1 && nq >= 0 && D > 0 && ldq >= D, "bad size");
+  QPG_CHECK_ARG(n_parts == 1 || part_stride >= (int64_t)nq * KB, "part_stride smaller than one part");
+  if (nq == 0) return QPG_OK;
+  QPG_CHECK_ARG(parts && packed && row_sqnorm && q_info && q && table && ranks, "null pointer");
+  sliced_resolve_kernel<<<nq, KB, 0, (cudaStream_t)stream>>>(parts, n_parts, (long long)part_stride, packed, (D + 127) / 128, D, row_sqnorm,
+                                                             first_id, q_info, q, ldq, reinterpret_cast<Pair*>(table),
+                                                             ranks, qflags, reinterpret_cast<unsigned long long*>(stats));
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}

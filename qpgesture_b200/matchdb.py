@@ -144,6 +144,82 @@ class PackedRows:
         return self.packed.numel() * 4
 
 
+def aligned_bytes(nbytes: int, device, align: int = 1024) -> torch.Tensor:
+    """uint8 device buffer whose data pointer is `align`-byte aligned (the UMMA tile images need 1024)."""
+    raw = torch.empty(max(int(nbytes), 1) + align, dtype=torch.uint8, device=device)
+    off = (-raw.data_ptr()) % align
+    return raw[off:off + max(int(nbytes), 1)]
+
+
+def bin_order(labels: torch.Tensor):
+    """Rows ordered by start code (stable, so ids ascend inside a bin); labels outside [0,512) go last.
+    -> (order int32 [W]: sorted position -> source row, bin_start int32 [513])"""
+    key = torch.where((labels >= 0) & (labels < codebook_size), labels, torch.full_like(labels, codebook_size))
+    skey, order = torch.sort(key.to(torch.int64), stable=True)
+    edges = torch.arange(codebook_size + 1, device=labels.device, dtype=torch.int64)
+    bin_start = torch.searchsorted(skey, edges)
+    return order.to(torch.int32).contiguous(), bin_start.to(torch.int32).contiguous()
+
+
+def column_exponents(rows: torch.Tensor):
+    """Per-column power-of-two scaling for the fixed-point copy: None when the columns already share a
+    magnitude (binary exponents of the column maxima within 2 of each other), else int8 [D] =
+    floor(log2(max |x[:, k]|)) - median."""
+    colmax = rows.abs().amax(dim=0).to(torch.float64)
+    ok = colmax > 0
+    if not bool(ok.any()):
+        return None
+    e = torch.floor(torch.log2(torch.where(ok, colmax, torch.ones_like(colmax))))
+    med = e[ok].median()
+    e = torch.where(ok, e - med, torch.zeros_like(e))
+    if float(e.max() - e.min()) < 3:
+        return None
+    return e.clamp(-60, 60).to(torch.int8).contiguous()
+
+
+@dataclass
+class SlicedRows:
+    """int8-sliced fixed-point copy of a float32 row table in bin order (csrc/sliced_scan.cu)."""
+    slices: torch.Tensor      # uint8, 1024-byte aligned tile images
+    row_info: torch.Tensor    # float64 [W, 2]
+    order: torch.Tensor       # int32 [W]
+    bin_start: torch.Tensor   # int32 [513]
+    col_exp: Optional[torch.Tensor]
+    W: int
+    D: int
+
+    @property
+    def n_kblocks(self) -> int:
+        return -(-self.D // 128)
+
+    @property
+    def Wpad(self) -> int:
+        return -(-self.W // 128) * 128
+
+    @staticmethod
+    def from_rows(rows: torch.Tensor, sqnorm: torch.Tensor, order: torch.Tensor, bin_start: torch.Tensor,
+                  column_scaling: bool = True) -> "SlicedRows":
+        """rows float32 [W, D] on the device (this shard, source order); sqnorm float64 [W] by source row."""
+        lib = _lib.load()
+        assert rows.is_cuda and rows.dtype == torch.float32 and rows.dim() == 2
+        rows = rows.contiguous()
+        W, D = rows.shape
+        dev = rows.device
+        col_exp = column_exponents(rows) if column_scaling and W > 0 else None
+        slices = aligned_bytes(lib.qpg_sliced_bytes(W, D), dev)
+        row_info = torch.zeros((max(W, 1), 2), dtype=torch.float64, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(lib.qpg_slice_rows_i8(_lib.ptr(rows), W, D, _lib.ptr(order), _lib.ptr(col_exp),
+                                             _lib.ptr(sqnorm.contiguous()), _lib.ptr(slices), _lib.ptr(row_info),
+                                             _lib.stream_ptr()), "qpg_slice_rows_i8")
+            torch.cuda.current_stream().synchronize()
+        return SlicedRows(slices, row_info, order, bin_start, col_exp, W, D)
+
+    @property
+    def nbytes(self) -> int:
+        return self.slices.numel()
+
+
 class MatchDatabase:
     """Everything the matcher kernels read, resident on one GPU."""
 
@@ -151,10 +227,14 @@ class MatchDatabase:
                  txt_rows: np.ndarray, aud_rows: Optional[np.ndarray] = None,
                  aud_tokens: Optional[np.ndarray] = None, freq_code: Optional[np.ndarray] = None,
                  freq_rank: Optional[np.ndarray] = None, pos_rank: Optional[np.ndarray] = None,
-                 device=None, seq_range=None, fuse_text=True):
+                 device=None, seq_range=None, fuse_text=False, sliced=True, replicate_exact=False):
         """aud_rows [N*26, Da] float32 (mode A) or aud_tokens [N*26, 11] ints (mode B);
         txt_rows [N*26, Dt] float32.  `seq_range=(j0, j1)` keeps only the windows of
-        sequences j0..j1-1 on this GPU (row shard); code / phase tables stay whole."""
+        sequences j0..j1-1 on this GPU (row shard); code / phase tables stay whole.
+        `sliced`: build the int8-sliced copies the one-pass scan streams (mode A).
+        `replicate_exact`: with a row shard, keep the float32 tables of ALL rows on this GPU (they are only
+        touched to re-evaluate undecided candidates) while the scanned, sliced copy holds the shard - every
+        rank can then settle cross-shard decisions itself after ONE all-gather."""
         assert mode in ("A", "B")
         _lib.load()
         self.mode = mode
@@ -169,29 +249,42 @@ class MatchDatabase:
         w0, w1 = j0 * WINDOWS_PER_SEQ, j1 * WINDOWS_PER_SEQ
         self.W = w1 - w0
         dev = self.device
+        self.replicated = bool(replicate_exact) and seq_range is not None
+        x0, x1 = (0, self.n_seq * WINDOWS_PER_SEQ) if self.replicated else (w0, w1)
+        self.exact_offset = x0               # global id of row 0 of the float32 tables
+        self.row_base = w0 - x0              # shard row r is row r + row_base of the float32 tables
 
         labels = code[:, :WINDOWS_PER_SEQ].reshape(-1).astype(np.int32)          # code_train[j, m]
-        self.labels = torch.from_numpy(np.ascontiguousarray(labels[w0:w1])).to(dev)
+        self.labels = torch.from_numpy(np.ascontiguousarray(labels[x0:x1])).to(dev)   # rows of the float32 tables
         self.code = torch.from_numpy(code.astype(np.int32)).contiguous().to(dev)
         self.phase_amp_host = np.ascontiguousarray(phase_amp, dtype=np.float32)
         assert self.phase_amp_host.shape == (self.n_seq, num_frames, 16)
         self.phase_amp = torch.from_numpy(self.phase_amp_host).to(dev)
 
         def local_rows(rows):
-            """host array of ALL windows (sliced to this shard here) or a CUDA tensor holding this shard only"""
+            """host array of ALL windows (cut to [x0, x1) here) or a CUDA tensor holding exactly those rows"""
             if isinstance(rows, torch.Tensor):
-                assert rows.is_cuda and rows.shape[0] == self.W, "device rows must be this rank's shard"
+                assert rows.is_cuda and rows.shape[0] == x1 - x0, "device rows must be the rows this rank keeps"
                 return rows.to(device=dev, dtype=torch.float32)
-            return torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float32)[w0:w1])).to(dev)
+            return torch.from_numpy(np.ascontiguousarray(np.asarray(rows, dtype=np.float32)[x0:x1])).to(dev)
+
+        shard = slice(self.row_base, self.row_base + self.W)
+        self.aud_s = self.txt_s = None
+        if sliced and mode == "A":
+            self.order, self.bin_start = bin_order(self.labels[shard])
 
         txt_dev = local_rows(txt_rows)
         self.txt = PackedRows.from_rows(txt_dev)
+        if sliced and mode == "A":
+            self.txt_s = SlicedRows.from_rows(txt_dev[shard], self.txt.sqnorm[shard], self.order, self.bin_start)
         self.aud = None
         self.tokens = None
         self.fused = None
         if mode == "A":
             aud_dev = local_rows(aud_rows)
             self.aud = PackedRows.from_rows(aud_dev)
+            if sliced:
+                self.aud_s = SlicedRows.from_rows(aud_dev[shard], self.aud.sqnorm[shard], self.order, self.bin_start)
             # audio | text in one table for the fused single-pass scan (qpg_cand_cosine2_minbycode)
             if fuse_text and aud_dev.shape[1] % 128 == 0 and txt_dev.shape[1] % 128 == 0 and \
                     self.W * 4 * (aud_dev.shape[1] + txt_dev.shape[1]) <= (8 << 30):
@@ -219,12 +312,18 @@ class MatchDatabase:
         self.pos_rank_host = np.asarray(pos_rank, dtype=np.int32)
         self.freq_rank = torch.from_numpy(self.freq_rank_host).to(dev)
         self.pos_rank = torch.from_numpy(np.ascontiguousarray(self.pos_rank_host)).to(dev)
+        # transposed int16 copy for qpg_match_lookup: [c][last], coalesced over `last`
+        self.pos_rank_t = torch.from_numpy(np.ascontiguousarray(self.pos_rank_host.T.astype(np.int16))).to(dev)
         torch.cuda.synchronize(dev)
 
     # -- bytes one query pass reads (the roofline's algorithmic bytes use D, not the padded D)
     def algorithmic_bytes(self, which: str) -> int:
         t = self.aud if which == "audio" else self.txt
         return self.W * (4 * t.D + 4)
+
+    @property
+    def n_exact_rows(self) -> int:
+        return self.aud.W if self.aud is not None else self.txt.W
 
     def payload(self, w: int) -> np.ndarray:
         j, m = divmod(int(w), WINDOWS_PER_SEQ)

@@ -472,9 +472,11 @@ def test_reference_call_path_predict_code_from_audio(tmp_path):
     # tail="numpy" replays the reference's own argsort calls: identical whenever this machine orders the
     # frequency-rank ties like the recording machine did
     from qpgesture_b200.matchdb import freq_rank_from_code
-    if np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
-        assert np.array_equal(pred, fx["knn_pred"])
     assert pred.shape == fx["knn_pred"].shape and pred.dtype == np.int64
+    if not np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
+        pytest.skip("NumPy on this machine orders the frequency-rank ties differently from the recording machine; "
+                    "only shape and dtype were checked")
+    assert np.array_equal(pred, fx["knn_pred"])
 
 
 @pytest.mark.parametrize("path", CASES)
@@ -495,8 +497,9 @@ def test_golden_mode_b_segment(path):
                                               clip_context=ctx, use_aud=True)
     assert codes.shape == (30,) and phases.shape == (8, 8, 16) and vote.shape == (8,)
     # integer Levenshtein ranks are dominated by ties; NumPy's tie order is platform defined
-    if np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
-        assert np.array_equal(codes, fx["codes_b"]) and np.array_equal(vote, fx["vote_b"])
+    if not np.array_equal(freq_rank_from_code(code), fx["freq_rank"]):
+        pytest.skip("NumPy on this machine orders ties differently from the recording machine; only shapes were checked")
+    assert np.array_equal(codes, fx["codes_b"]) and np.array_equal(vote, fx["vote_b"])
 
 
 def test_device_feature_stacking_bit_exact():

@@ -1,0 +1,128 @@
+#!/usr/bin/env python
+"""Stage-by-stage timing of the one-pass matcher step (sliced engine) on one GPU.
+
+    python tools/bench_sliced.py [--n-seq 512] [--clips 1] [--reps 50]
+
+Prints one JSON object: per-stage CUDA-event times (each stage timed alone, back to back `reps` times, table
+larger than L2 so every scan pass streams from HBM), the captured-graph step time, and the float64 engine
+for comparison."""
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-seq", type=int, default=512)
+    ap.add_argument("--clips", type=int, default=1)
+    ap.add_argument("--n-seg", type=int, default=6)
+    ap.add_argument("--wavlm-dim", type=int, default=1024)
+    ap.add_argument("--ctx-dim", type=int, default=384)
+    ap.add_argument("--reps", type=int, default=50)
+    ap.add_argument("--no-f64", action="store_true")
+    a = ap.parse_args()
+    import torch
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import MatchDatabase
+
+    dev = torch.device("cuda")
+    lib = _lib.load()
+    rng = np.random.default_rng(0)
+    n = a.n_seq
+    code = rng.integers(0, 512, size=(n, 30)).astype(np.int64)
+    sig = rng.standard_normal((512, 135)).astype(np.float32)
+    phase_amp = rng.standard_normal((n, 240, 16)).astype(np.float32)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1)
+    aud = torch.randn((n * 26, 6 * a.wavlm_dim), device=dev, generator=g)
+    txt = torch.randn((n * 26, a.ctx_dim), device=dev, generator=g)
+    db = MatchDatabase("A", code, sig, phase_amp, txt, aud_rows=aud, device=dev)
+    del aud, txt
+    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, tail="device")
+    out = dict(n_seq=n, windows=n * 26, clips=a.clips, steps=a.clips * a.n_seg * 8)
+
+    def timed(fn, reps=a.reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps * 1e3      # us
+
+    for engine in (("sliced",) if a.no_f64 else ("sliced", "f64")):
+        p = knn.make_plan(a.clips, a.n_seg, use_graph=True, engine=engine)
+        p.qa.copy_(torch.randn(p.qa.shape, device=dev, generator=g))
+        p.qt.copy_(torch.randn(p.qt.shape, device=dev, generator=g))
+        p.seed_code.fill_(7)
+        p.seed_phase.copy_(torch.randn(p.seed_phase.shape, device=dev, generator=g))
+        out[engine + "_graph_us"] = timed(lambda: knn.run_plan(p))
+        out[engine + "_status"] = p.status.cpu().tolist()
+        if engine != "sliced":
+            continue
+        out["passes"] = len(p.passes)
+        out["stats_per_step"] = [int(x) // (a.reps + 3 + 2) for x in p.stats.cpu().tolist()]
+        sp = _lib.stream_ptr()
+        A, T = db.aud_s, db.txt_s
+        ps = p.passes[0]
+        qa, qt = p.qa[ps.q0:ps.q0 + ps.nq], p.qt[ps.q0:ps.q0 + ps.nq]
+        qia, qit = p.qinfo_a[ps.q0:ps.q0 + ps.nq], p.qinfo_t[ps.q0:ps.q0 + ps.nq]
+
+        def slice_q():
+            lib.qpg_slice_queries_i8(_lib.ptr(qa), ps.nq, A.D, A.D, _lib.ptr(A.col_exp), ps.n_pad, _lib.ptr(ps.qs_a), _lib.ptr(qia), sp)
+            lib.qpg_slice_queries_i8(_lib.ptr(qt), ps.nq, T.D, T.D, _lib.ptr(T.col_exp), ps.n_pad, _lib.ptr(ps.qs_t), _lib.ptr(qit), sp)
+        segs = (_lib.SlicedSeg * 2)()
+        segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.data_ptr(), ps.qs_a.data_ptr(), p.sacc_a.data_ptr(), A.n_kblocks
+        segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
+
+        def zero():
+            p.sacc_a.zero_()
+            p.sacc_t.zero_()
+
+        def scan():
+            lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp)
+
+        def scan_audio_only():
+            lib.qpg_sliced_scan_i8(segs, 1, A.W, ps.n_pad, ps.nq, sp)
+
+        def bins():
+            for x, (S, E, sacc, q, qi) in enumerate(((A, db.aud, p.sacc_a, qa, qia), (T, db.txt, p.sacc_t, qt, qit))):
+                lib.qpg_sliced_bins(_lib.ptr(sacc), S.W, ps.nq, _lib.ptr(S.bin_start), _lib.ptr(S.row_info), _lib.ptr(S.order),
+                                    _lib.ptr(E.sqnorm), db.id_offset, db.row_base, _lib.ptr(qi), _lib.ptr(E.packed), S.D,
+                                    _lib.ptr(q), S.D, _lib.ptr(p.bins[x, ps.q0:ps.q0 + ps.nq]), None, sp)
+
+        def resolve():
+            for x, (E, q, qi, tab, rk, qf) in enumerate(((db.aud, p.qa, p.qinfo_a, p.ta, p.ra, p.qfa), (db.txt, p.qt, p.qinfo_t, p.tt, p.rt, p.qft))):
+                lib.qpg_sliced_resolve(_lib.ptr(p.parts[0, x]), 1, 2 * p.Q * 512, p.Qt, _lib.ptr(E.packed), E.D, _lib.ptr(E.sqnorm),
+                                       db.exact_offset, _lib.ptr(qi), _lib.ptr(q), E.D, _lib.ptr(tab), _lib.ptr(rk), _lib.ptr(qf), None, sp)
+
+        def lookup():
+            lib.qpg_match_lookup(_lib.ptr(p.ta), _lib.ptr(p.tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank_t), _lib.ptr(db.freq_rank),
+                                 _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft),
+                                 p.Qt, _lib.ptr(p.entries), sp)
+
+        def walk():
+            lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
+                               p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
+        stages = dict(slice_queries=slice_q, zero_sacc=zero, scan=scan, scan_audio_only=scan_audio_only, bins=bins,
+                      resolve=resolve, lookup=lookup, walk=walk)
+        out["stage_us"] = {k: timed(f) for k, f in stages.items()}
+        sliced_bytes = A.nbytes + T.nbytes
+        alg_bytes = db.W * (4 * (db.aud.D + db.txt.D) + 4)
+        out["scan_GBps_sliced_bytes"] = sliced_bytes / out["stage_us"]["scan"] / 1e3
+        out["scan_GBps_algorithmic"] = alg_bytes / out["stage_us"]["scan"] / 1e3
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
