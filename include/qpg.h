@@ -145,6 +145,33 @@ typedef struct {
   int32_t n_kblocks;       /* ceil(D/128)                                      */
   int32_t pad;
 } qpg_sliced_seg_t;
+typedef struct {
+  const float* q;          /* float32 [Q, ldq]                                   */
+  const int8_t* col_exp;   /* the table's column exponents (NULL if none)        */
+  int8_t* q_slices;        /* out, 1024-byte aligned, qpg_sliced_query_bytes()   */
+  qpg_qinfo_t* q_info;     /* out [Q]                                            */
+  int64_t ldq;
+  int32_t D;
+  int32_t pad;
+} qpg_slice_job_t;
+/* one table (feature block) as the bins / resolve stages see it */
+typedef struct {
+  const float* packed;         /* float32 tile table of qpg_pack_rows_f32 (exact re-evaluation)          */
+  const double* row_sqnorm;    /* its squared norms                                                       */
+  const float* q;              /* float32 queries [nq, ldq]                                               */
+  const qpg_qinfo_t* q_info;   /* [nq] from qpg_slice_queries_i8                                          */
+  int64_t ldq;
+  int32_t D;
+  int32_t pad;
+  int64_t* sacc;               /* bins: scan output [n_pad][ceil(W/128)*128]                              */
+  const int32_t* bin_start;    /* bins: [513]                                                             */
+  const void* row_info;        /* bins: from qpg_slice_rows_i8                                            */
+  const int32_t* order;        /* bins: [W]                                                               */
+  qpg_bin_t* bins;             /* bins: out [nq][512];  resolve: in, part 0 (part p = + p*part_stride)    */
+  qpg_pair_t* table;           /* resolve: out [nq][512]                                                  */
+  int32_t* ranks;              /* resolve: out [nq][512]                                                  */
+  int32_t* qflags;             /* resolve: out [nq] (may be NULL)                                         */
+} qpg_sliced_table_t;
 size_t qpg_sliced_bytes(int64_t n_rows, int D);
 size_t qpg_sliced_query_bytes(int D, int n_pad);
 /* rows float32 [W, D] row-major; col_exp int8 [D] optional per-column power-of-two scaling (database rows
@@ -153,9 +180,8 @@ size_t qpg_sliced_query_bytes(int D, int n_pad);
  * row_info 16 bytes per sorted row (opaque).  slices must be 1024-byte aligned. */
 int qpg_slice_rows_i8(const float* rows, int64_t W, int D, const int32_t* order, const int8_t* col_exp,
                       const double* row_sqnorm, int8_t* slices, void* row_info, void* stream);
-/* q float32 [Q, ldq]; n_pad in {16,32,48,64} >= Q */
-int qpg_slice_queries_i8(const float* q, int Q, int D, int64_t ldq, const int8_t* col_exp, int n_pad,
-                         int8_t* q_slices, qpg_qinfo_t* q_info, void* stream);
+/* the Q query steps of one pass, 1 or 2 feature blocks in one launch; n_pad in {16,32,48,64} >= Q */
+int qpg_slice_queries_i8(const qpg_slice_job_t* jobs, int n_jobs, int Q, int n_pad, void* stream);
 /* the pass itself: 1 or 2 feature blocks (audio, text) of the same W rows in one launch (stream-K over
  * row tiles x k-blocks, int64 global accumulation: exact and order independent) */
 int qpg_sliced_scan_i8(const qpg_sliced_seg_t* segs, int n_segs, int64_t W, int n_pad, int nq, void* stream);
@@ -163,21 +189,19 @@ int qpg_sliced_scan_i8(const qpg_sliced_seg_t* segs, int n_segs, int64_t W, int 
  * 0, q_stride, 2*q_stride, ... < nq only */
 int qpg_sliced_scan_ref(const int8_t* db_slices, const int8_t* q_slices, int n_kblocks, int64_t W, int n_pad, int nq,
                         int q_stride, int64_t* sacc, void* stream);
-/* per (query, start code) records from sacc; bins with more than one possible winner are re-evaluated in
- * float64 right here.  packed/row_sqnorm: float32 tile table + norms; source row r of this (sliced) shard is row
- * r + row_base there and has global window id id_offset + r.
- * stats (optional, uint64[2]): [0] += rows re-evaluated here, [1] += bins decided in qpg_sliced_resolve */
-int qpg_sliced_bins(const int64_t* sacc, int64_t W, int nq, const int32_t* bin_start, const void* row_info,
-                    const int32_t* order, const double* row_sqnorm, int64_t id_offset, int64_t row_base,
-                    const qpg_qinfo_t* q_info, const float* packed, int D, const float* q, int64_t ldq,
-                    qpg_bin_t* bins_out, uint64_t* stats, void* stream);
+/* per (table, query, start code) records from sacc; bins with more than one possible winner are re-evaluated in
+ * float64 right here.  Source row r of this (sliced) shard is row r + row_base of packed / row_sqnorm and has
+ * global window id id_offset + r.  consume != 0: every sacc entry is zeroed once read (the next pass then needs
+ * no memset).  stats (optional, uint64[2]): [0] += rows re-evaluated here, [1] += bins decided in
+ * qpg_sliced_resolve */
+int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64_t W, int nq, int64_t id_offset, int64_t row_base,
+                    int consume, uint64_t* stats, void* stream);
 /* merge n_parts record sets (row shards), decide cross-shard winners and overlapping bins in float64, emit the
  * final table, its stable rank transform (= qpg_rank512) and per-query flags (bit 0: exact tie between
- * non-empty bins, i.e. the reference's argsort order is platform defined there).  Part p, query q, code c is
- * parts[p*part_stride + q*512 + c].  packed/row_sqnorm address rows by (global id - first_id). */
-int qpg_sliced_resolve(const qpg_bin_t* parts, int n_parts, int64_t part_stride, int nq, const float* packed, int D,
-                       const double* row_sqnorm, int64_t first_id, const qpg_qinfo_t* q_info, const float* q,
-                       int64_t ldq, qpg_pair_t* table, int32_t* ranks, int32_t* qflags, uint64_t* stats, void* stream);
+ * non-empty bins, i.e. the reference's argsort order is platform defined there).  packed / row_sqnorm address
+ * rows by (global id - first_id). */
+int qpg_sliced_resolve(const qpg_sliced_table_t* tabs, int n_tabs, int n_parts, int64_t part_stride, int nq,
+                       int64_t first_id, uint64_t* stats, void* stream);
 
 /* ---------------- candidate distance, Levenshtein, fused min-by-code -----
  * tokens [W, 12] uint32 (11 used: g0*320+g1 per tap, GestureKNN.py:58-60),
@@ -256,8 +280,12 @@ int qpg_match_tail_segments(const qpg_pair_t* aud_table, const qpg_pair_t* txt_t
  * GestureKNN.py:540-555,:574-576 and what hangs off the chosen windows, as 32-byte entries [Q][512].
  * pos_rank_t is the TRANSPOSED pose rank table, int16 [512 c][512 last]; ranks/tables as produced by
  * qpg_rank512 / qpg_sliced_resolve; qflags_* (optional) per-step tie flags of qpg_sliced_resolve.
- * qpg_match_walk: one thread block per clip follows the entries (GestureKNN.py:627-660, segments chained as
- * :791,:800).  codes_out is pre-filled with -1, so a clip that stops early is recognisable.
+ * qpg_match_walk: follows the entries (GestureKNN.py:627-660, segments chained as :791,:800).  With `trans`
+ * (int16 [n_clips*n_seg*8][1024] scratch, 16-byte aligned; n_seg <= 13) the phase pick is first evaluated for
+ * EVERY reachable state in parallel and the sequential part is a shared-memory table walk (lowest latency, the
+ * choice for a few clips); with trans == NULL one warp per clip walks directly (two dependent loads per step,
+ * the choice for many clips).  Both give identical results.  codes_out is pre-filled with -1, so a clip that
+ * stops early is recognisable.
  * status_out[clip]: bit 0 (1) = a chosen start code had no window (the reference raises IndexError at :631);
  *                   bit 1 (2) = the result depended on the order of exact ties, which the reference leaves to
  *                   NumPy's unstable argsort (this implementation: lower code first). */
@@ -266,8 +294,8 @@ int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, c
                      int64_t n_seq, const int32_t* aud_frame, const int32_t* txt_frame, const int32_t* qflags_a,
                      const int32_t* qflags_t, int Q, void* entries, void* stream);
 int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp, const int32_t* seed_code,
-                   const float* seed_phase, int n_clips, int n_seg, int64_t* codes_out, int32_t* vote_out,
-                   float* phase_out, int32_t* status_out, void* stream);
+                   const float* seed_phase, int n_clips, int n_seg, int16_t* trans, int64_t* codes_out,
+                   int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream);
 
 /* ---------------- VQ codebook L2 argmin -----------------------------------
  * BottleneckBlock.quantise (codebook/models/bottleneck.py:120-126):

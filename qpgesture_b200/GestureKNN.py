@@ -360,6 +360,10 @@ class CodeKNN(object):
             p.qfa = torch.zeros((Qt,), dtype=torch.int32, device=dev)
             p.qft = torch.zeros((Qt,), dtype=torch.int32, device=dev)
             p.entries = torch.empty((max(Qt, 1), codebook_size, 4), dtype=torch.int64, device=dev)   # 32-byte entries
+            # few clips: evaluate the phase pick for every reachable state in parallel, walk a table (lowest latency);
+            # many clips: one warp per clip walks directly (the clips hide each other's latency)
+            p.trans = torch.empty((Qt, 1024), dtype=torch.int16, device=dev) \
+                if (0 < n_tail <= MAX_TABLE_WALK_CLIPS and n_seg * STEPS_PER_SEGMENT <= 104) else None
             p.codes = torch.empty((n_tail, n_seg, num_frames_code), dtype=torch.int64, device=dev)
             p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
             p.status = torch.zeros((n_tail,), dtype=torch.int32, device=dev)
@@ -381,45 +385,54 @@ class CodeKNN(object):
                                                   _lib.ptr(q), nq, _lib.ptr(ta), _lib.ptr(tt), sp),
                    "qpg_cand_cosine2_minbycode")
 
+    def _sliced_tables(self, p, q0, nq, bins_q0, for_resolve=False):
+        """ctypes descriptors (audio, text) of qpg_sliced_table_t for queries [q0, q0+nq); `bins_q0` = first
+        query of the bins block the descriptor points at."""
+        db = self.db
+        tabs = (_lib.SlicedTable * 2)()
+        for x, (S, E, sacc, q, qi, tab, rk, qf) in enumerate((
+                (db.aud_s, db.aud, p.sacc_a, p.qa, p.qinfo_a, p.ta, p.ra, p.qfa),
+                (db.txt_s, db.txt, p.sacc_t, p.qt, p.qinfo_t, p.tt, p.rt, p.qft))):
+            t = tabs[x]
+            t.packed, t.row_sqnorm = _lib.dptr(E.packed), _lib.dptr(E.sqnorm)
+            t.q, t.q_info, t.ldq, t.D = _lib.dptr(q[q0:q0 + nq]), _lib.dptr(qi[q0:q0 + nq]), E.D, E.D
+            t.sacc, t.bin_start, t.row_info, t.order = _lib.dptr(sacc), _lib.dptr(S.bin_start), _lib.dptr(S.row_info), \
+                _lib.dptr(S.order)
+            t.bins = _lib.dptr(p.parts[0, x, bins_q0:bins_q0 + nq]) if for_resolve else \
+                _lib.dptr(p.bins[x, bins_q0:bins_q0 + nq])
+            if for_resolve:
+                t.table, t.ranks, t.qflags = _lib.dptr(tab), _lib.dptr(rk), _lib.dptr(qf)
+        return tabs
+
     def _launch_sliced(self, p, sp):
-        """slice queries -> one tensor-core pass per <= 64 steps -> per-bin records -> [all-gather] -> resolve."""
+        """slice queries -> one tensor-core pass per <= 64 steps -> per-bin records -> [all-gather] -> resolve:
+        four launches per pass-group on one GPU, audio and text handled together in each."""
         lib, db = _lib.load(), self.db
         A, T = db.aud_s, db.txt_s
-        col_a, col_t = _lib.ptr(A.col_exp), _lib.ptr(T.col_exp)
         for ps in p.passes:
-            qa, qt = p.qa[ps.q0:ps.q0 + ps.nq], p.qt[ps.q0:ps.q0 + ps.nq]
-            qia, qit = p.qinfo_a[ps.q0:ps.q0 + ps.nq], p.qinfo_t[ps.q0:ps.q0 + ps.nq]
-            _lib.check(lib.qpg_slice_queries_i8(_lib.ptr(qa), ps.nq, A.D, A.D, col_a, ps.n_pad, _lib.ptr(ps.qs_a),
-                                                _lib.ptr(qia), sp), "qpg_slice_queries_i8")
-            _lib.check(lib.qpg_slice_queries_i8(_lib.ptr(qt), ps.nq, T.D, T.D, col_t, ps.n_pad, _lib.ptr(ps.qs_t),
-                                                _lib.ptr(qit), sp), "qpg_slice_queries_i8")
-            p.sacc_a.zero_()
-            p.sacc_t.zero_()
+            jobs = (_lib.SliceJob * 2)()
+            for x, (S, q, qi, qs) in enumerate(((A, p.qa, p.qinfo_a, ps.qs_a), (T, p.qt, p.qinfo_t, ps.qs_t))):
+                jobs[x].q, jobs[x].col_exp = _lib.dptr(q[ps.q0:ps.q0 + ps.nq]), _lib.dptr(S.col_exp)
+                jobs[x].q_slices, jobs[x].q_info = _lib.dptr(qs), _lib.dptr(qi[ps.q0:ps.q0 + ps.nq])
+                jobs[x].ldq, jobs[x].D = S.D, S.D
+            _lib.check(lib.qpg_slice_queries_i8(jobs, 2, ps.nq, ps.n_pad, sp), "qpg_slice_queries_i8")
             segs = (_lib.SlicedSeg * 2)()
             segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = \
                 A.slices.data_ptr(), ps.qs_a.data_ptr(), p.sacc_a.data_ptr(), A.n_kblocks
             segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = \
                 T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
+            # sacc is all zero here: zero-initialised by make_plan and re-zeroed by every bins stage (consume = 1)
             _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "qpg_sliced_scan_i8")
-            for x, (S, E, sacc, q, qi) in enumerate(((A, db.aud, p.sacc_a, qa, qia), (T, db.txt, p.sacc_t, qt, qit))):
-                _lib.check(lib.qpg_sliced_bins(_lib.ptr(sacc), S.W, ps.nq, _lib.ptr(S.bin_start), _lib.ptr(S.row_info),
-                                               _lib.ptr(S.order), _lib.ptr(E.sqnorm), db.id_offset, db.row_base,
-                                               _lib.ptr(qi), _lib.ptr(E.packed), S.D, _lib.ptr(q), S.D,
-                                               _lib.ptr(p.bins[x, ps.q0:ps.q0 + ps.nq]), _lib.ptr(p.stats), sp),
-                           "qpg_sliced_bins")
+            _lib.check(lib.qpg_sliced_bins(self._sliced_tables(p, ps.q0, ps.nq, ps.q0), 2, A.W, ps.nq, db.id_offset,
+                                           db.row_base, 1, _lib.ptr(p.stats), sp), "qpg_sliced_bins")
         if p.world > 1:
             import torch.distributed as dist
             dist.all_gather_into_tensor(p.parts, p.bins, group=self.process_group)     # the ONE data-path collective
         per_clip = p.n_seg * STEPS_PER_SEGMENT
         q0, q1 = p.tail.start * per_clip, p.tail.stop * per_clip
         stride = 2 * p.Q * codebook_size                                               # records between two parts
-        for x, (E, q, qi, tab, rk, qf) in enumerate(((db.aud, p.qa, p.qinfo_a, p.ta, p.ra, p.qfa),
-                                                     (db.txt, p.qt, p.qinfo_t, p.tt, p.rt, p.qft))):
-            parts = p.parts[0, x, q0:q1]
-            _lib.check(lib.qpg_sliced_resolve(_lib.ptr(parts), p.world, stride, q1 - q0, _lib.ptr(E.packed), E.D,
-                                              _lib.ptr(E.sqnorm), db.exact_offset, _lib.ptr(qi[q0:q1]), _lib.ptr(q[q0:q1]),
-                                              E.D, _lib.ptr(tab), _lib.ptr(rk), _lib.ptr(qf), _lib.ptr(p.stats), sp),
-                       "qpg_sliced_resolve")
+        _lib.check(lib.qpg_sliced_resolve(self._sliced_tables(p, q0, q1 - q0, q0, for_resolve=True), 2, p.world, stride,
+                                          q1 - q0, db.exact_offset, _lib.ptr(p.stats), sp), "qpg_sliced_resolve")
         return p.ta, p.tt
 
     def _launch_f64(self, p, sp):
@@ -468,8 +481,8 @@ class CodeKNN(object):
                                         _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft), p.Qt,
                                         _lib.ptr(p.entries), sp), "qpg_match_lookup")
         _lib.check(lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
-                                      _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote),
-                                      _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
+                                      _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes),
+                                      _lib.ptr(p.vote), _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
 
     def run_plan(self, p):
         """Enqueue one step on the current stream (graph replay when the plan was captured)."""
@@ -507,9 +520,11 @@ class CodeKNN(object):
                                             _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame),
                                             _lib.ptr(db.txt_frame), _lib.ptr(qfa), _lib.ptr(qft), Q, _lib.ptr(entries), sp),
                        "qpg_match_lookup")
+            trans = torch.empty((Q, 1024), dtype=torch.int16, device=dev) \
+                if (n_clips <= MAX_TABLE_WALK_CLIPS and n_seg * STEPS_PER_SEGMENT <= 104) else None
             _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
-                                          _lib.ptr(sph), n_clips, n_seg, _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(phase),
-                                          _lib.ptr(status), sp), "qpg_match_walk")
+                                          _lib.ptr(sph), n_clips, n_seg, _lib.ptr(trans), _lib.ptr(codes), _lib.ptr(vote),
+                                          _lib.ptr(phase), _lib.ptr(status), sp), "qpg_match_walk")
         return codes, vote, phase, status
 
     def _tail_numpy_segment(self, ta_np, tt_np, seed_code, seed_phase, desired_k=0, use_txt=True, use_aud=True):
@@ -672,6 +687,9 @@ class CodeKNN(object):
                 out[b, g] = codes
                 code0, ph0 = int(codes[-1]), phases[-1]
         return out
+
+
+MAX_TABLE_WALK_CLIPS = 2
 
 
 def _phase_ntc(phase_train):

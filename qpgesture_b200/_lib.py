@@ -40,6 +40,23 @@ class SlicedSeg(C.Structure):
                 ("pad", C.c_int32)]
 
 
+class SliceJob(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("col_exp", C.c_void_p), ("q_slices", C.c_void_p), ("q_info", C.c_void_p),
+                ("ldq", C.c_int64), ("D", C.c_int32), ("pad", C.c_int32)]
+
+
+class SlicedTable(C.Structure):
+    _fields_ = [("packed", C.c_void_p), ("row_sqnorm", C.c_void_p), ("q", C.c_void_p), ("q_info", C.c_void_p),
+                ("ldq", C.c_int64), ("D", C.c_int32), ("pad", C.c_int32), ("sacc", C.c_void_p),
+                ("bin_start", C.c_void_p), ("row_info", C.c_void_p), ("order", C.c_void_p), ("bins", C.c_void_p),
+                ("table", C.c_void_p), ("ranks", C.c_void_p), ("qflags", C.c_void_p)]
+
+
+def dptr(t):
+    """raw device address (int) of a tensor, 0 for None - for ctypes struct fields"""
+    return 0 if t is None else ptr(t).value
+
+
 _P = C.c_void_p
 _I64 = C.c_int64
 _INT = C.c_int
@@ -61,13 +78,13 @@ SIGNATURES = {
     "qpg_sliced_bytes": (C.c_size_t, [_I64, _INT]),
     "qpg_sliced_query_bytes": (C.c_size_t, [_INT, _INT]),
     "qpg_slice_rows_i8": (_INT, [_P, _I64, _INT, _P, _P, _P, _P, _P, _P]),
-    "qpg_slice_queries_i8": (_INT, [_P, _INT, _INT, _I64, _P, _INT, _P, _P, _P]),
+    "qpg_slice_queries_i8": (_INT, [_P, _INT, _INT, _INT, _P]),
     "qpg_sliced_scan_i8": (_INT, [_P, _INT, _I64, _INT, _INT, _P]),
     "qpg_sliced_scan_ref": (_INT, [_P, _P, _INT, _I64, _INT, _INT, _INT, _P, _P]),
-    "qpg_sliced_bins": (_INT, [_P, _I64, _INT, _P, _P, _P, _P, _I64, _I64, _P, _P, _INT, _P, _I64, _P, _P, _P]),
-    "qpg_sliced_resolve": (_INT, [_P, _INT, _I64, _INT, _P, _INT, _P, _I64, _P, _P, _I64, _P, _P, _P, _P, _P]),
+    "qpg_sliced_bins": (_INT, [_P, _INT, _I64, _INT, _I64, _I64, _INT, _P, _P]),
+    "qpg_sliced_resolve": (_INT, [_P, _INT, _INT, _I64, _INT, _I64, _P, _P]),
     "qpg_match_lookup": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
-    "qpg_match_walk": (_INT, [_P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
+    "qpg_match_walk": (_INT, [_P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
     "qpg_l2_prefetch": (_INT, [_P, C.c_size_t, _P]),

@@ -35,8 +35,8 @@ struct __align__(16) Entry {
 };
 static_assert(sizeof(Entry) == 32, "entry is 32 bytes");
 
-// grid (Q, 4), 128 threads: thread = one value of `last`
-__global__ void __launch_bounds__(128)
+// grid (Q, 16), 256 threads: lane = one of 32 values of `last`, warp = one 64-code slice of the scan
+__global__ void __launch_bounds__(256)
     match_lookup_kernel(const Pair* __restrict__ aud_table, const Pair* __restrict__ txt_table,
                         const int32_t* __restrict__ aud_rank, const int32_t* __restrict__ txt_rank,
                         const int16_t* __restrict__ pos_rank_t, const int32_t* __restrict__ freq_rank,
@@ -44,14 +44,16 @@ __global__ void __launch_bounds__(128)
                         const int32_t* __restrict__ txt_frame, const int32_t* __restrict__ qflags_a,
                         const int32_t* __restrict__ qflags_t, Entry* __restrict__ entries) {
   constexpr int EMPTY = 1 << 30;
-  __shared__ int s_key[2][KB];          // 20*rank + freq_rank per table; empty bins carry the EMPTY bit
+  constexpr int NSL = 8, CPS = KB / NSL;        // slices, codes per slice
+  __shared__ int s_key[2][KB];                  // 20*rank + freq_rank per table; empty bins carry the EMPTY bit
   __shared__ int s_fr[KB];
   __shared__ int s_ne[2];
-  const int q = blockIdx.x, tid = threadIdx.x;
-  const int last = blockIdx.y * 128 + tid;
+  __shared__ int p_best[NSL][2][32], p_arg[NSL][2][32], p_ties[NSL][2][32], p_bne[NSL][2][32], p_lbe[NSL][2][32];
+  const int q = blockIdx.x, tid = threadIdx.x, l = tid & 31, sl = tid >> 5;
+  const int last = blockIdx.y * 32 + l;
   if (tid < 2) s_ne[tid] = 0;
   __syncthreads();
-  for (int c = tid; c < KB; c += 128) {
+  for (int c = tid; c < KB; c += 256) {
     const int fr = freq_rank[c];
     const long long ida = (long long)aud_table[(size_t)q * KB + c].id, idt = (long long)txt_table[(size_t)q * KB + c].id;
     s_fr[c] = fr;
@@ -66,23 +68,56 @@ __global__ void __launch_bounds__(128)
   int best[2] = {0x7fffffff, 0x7fffffff}, arg[2] = {0, 0}, ties[2] = {0, 0};
   int best_ne[2] = {0x7fffffff, 0x7fffffff};       // best key over non-empty bins
   int lb_e[2] = {0x3fffffff, 0x3fffffff};          // min over empty bins of 20*pos + freq
-#pragma unroll 4
-  for (int c = 0; c < KB; ++c) {
-    const int p20 = 20 * (int)pos_rank_t[(size_t)c * KB + last];
-    const int fr = s_fr[c];
+  {
+    const int c0 = sl * CPS;
+    int pr[CPS];
+#pragma unroll
+    for (int i = 0; i < CPS; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
+#pragma unroll
+    for (int i = 0; i < CPS; ++i) {
+      const int c = c0 + i;
+      const int p20 = 20 * pr[i];
+      const int fr = s_fr[c];
+#pragma unroll
+      for (int x = 0; x < 2; ++x) {
+        const int sk = s_key[x][c];
+        const int key = p20 + (sk & ~EMPTY);
+        if (key < best[x]) {
+          best[x] = key;
+          arg[x] = c;
+          ties[x] = 1;
+        } else if (key == best[x]) {
+          ++ties[x];
+        }
+        if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
+        else best_ne[x] = min(best_ne[x], key);
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 2; ++x) {
+    p_best[sl][x][l] = best[x];
+    p_arg[sl][x][l] = arg[x];
+    p_ties[sl][x][l] = ties[x];
+    p_bne[sl][x][l] = best_ne[x];
+    p_lbe[sl][x][l] = lb_e[x];
+  }
+  __syncthreads();
+  if (sl != 0) return;
+  // combine the slices in ascending code order: the first minimum keeps the arg
+  for (int s2 = 1; s2 < NSL; ++s2) {
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-      const int sk = s_key[x][c];
-      const int key = p20 + (sk & ~EMPTY);
-      if (key < best[x]) {
-        best[x] = key;
-        arg[x] = c;
-        ties[x] = 1;
-      } else if (key == best[x]) {
-        ++ties[x];
+      const int b = p_best[s2][x][l];
+      if (b < best[x]) {
+        best[x] = b;
+        arg[x] = p_arg[s2][x][l];
+        ties[x] = p_ties[s2][x][l];
+      } else if (b == best[x]) {
+        ties[x] += p_ties[s2][x][l];
       }
-      if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
-      else best_ne[x] = min(best_ne[x], key);
+      best_ne[x] = min(best_ne[x], p_bne[s2][x][l]);
+      lb_e[x] = min(lb_e[x], p_lbe[s2][x][l]);
     }
   }
   Entry e;
@@ -132,13 +167,6 @@ __global__ void __launch_bounds__(128)
   entries[(size_t)q * KB + last] = e;
 }
 
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ void bar64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
-
 __device__ __forceinline__ Entry load_entry(const Entry* p) {
   const int4* q = reinterpret_cast<const int4*>(p);
   const int4 a = __ldg(q), b = __ldg(q + 1);
@@ -155,27 +183,65 @@ __device__ __forceinline__ Entry load_entry(const Entry* p) {
   return e;
 }
 
-// one CTA (2 warps) per clip: warp 0 scores the audio candidate, warp 1 the text candidate
-__global__ void __launch_bounds__(64)
+// The pick of GestureKNN.py:627-646 by ONE warp: lanes 0-15 score the audio candidate, lanes 16-31 the text
+// candidate; lane (hl = lane & 15) owns column hl of the 8 x 16 phase|amplitude block:
+//   a = [prev[3..7]; head[0..2]],  b = [prev[5..7]; head[0..4]]   (rows; :636,:644)
+//   dist = 0.5 * || a/|a| - b/|b| ||^2   (sklearn paired cosine distance, float64, all-zero vector -> norm 1)
+// prev5[k] = prev[3 + k][hl] (k < 5) is passed in registers, head rows come from `head` (row stride PC).
+// Fixed summation order (8 terms per lane, then a 16-lane butterfly); returns 0 (audio, also on ties) or 1.
+__device__ __forceinline__ int phase_pick(const float (&prev5)[5], const float* __restrict__ head, int lane) {
+  const int hl = lane & 15;
+  float h[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) h[k] = head[k * PC + hl];
+  double av[8], bv[8], sa = 0.0, sb = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    av[k] = (double)(k < 5 ? prev5[k] : h[k - 5]);
+    bv[k] = (double)(k < 3 ? prev5[k + 2] : h[k - 3]);
+    sa = fma(av[k], av[k], sa);
+    sb = fma(bv[k], bv[k], sb);
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    sa += __shfl_xor_sync(0xffffffffu, sa, o);
+    sb += __shfl_xor_sync(0xffffffffu, sb, o);
+  }
+  const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
+  double acc = 0.0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const double d = av[k] / na - bv[k] / nb;
+    acc = fma(d, d, acc);
+  }
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  const double dist = 0.5 * acc;
+  const double d_a = __shfl_sync(0xffffffffu, dist, 0), d_t = __shfl_sync(0xffffffffu, dist, 16);
+  return d_a <= d_t ? 0 : 1;                                  // tmp_distance.index(min(...)): audio wins ties (:646)
+}
+
+// ---- direct walk: one warp per clip, two dependent loads per step (many clips: latency hidden across clips) ----
+__global__ void __launch_bounds__(32)
     match_walk_kernel(const Entry* __restrict__ entries, const int32_t* __restrict__ code,
                       const float* __restrict__ phase_amp, const int32_t* __restrict__ seed_code,
                       const float* __restrict__ seed_phase, int n_seg, int64_t* __restrict__ codes_out,
                       int32_t* __restrict__ vote_out, float* __restrict__ phase_out, int32_t* __restrict__ status_out) {
-  __shared__ float prev[8 * PC];
-  __shared__ double s_dist[2];
-  const int b = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x, lane = threadIdx.x, hw = lane >> 4, hl = lane & 15;
   const int n_steps = n_seg * 8;
   const size_t q0 = (size_t)b * n_steps;
-  for (int e = threadIdx.x; e < 8 * PC; e += 64) prev[e] = seed_phase[(size_t)b * 8 * PC + e];
-  for (int i = threadIdx.x; i < n_seg * NCODE; i += 64) codes_out[(size_t)b * n_seg * NCODE + i] = -1;
-  int last = seed_code[b];
-  int status = 0;
-  if ((unsigned)last >= (unsigned)KB) {
-    if (threadIdx.x == 0) status_out[b] = 1;
+  for (int i = lane; i < n_seg * NCODE; i += 32) codes_out[(size_t)b * n_seg * NCODE + i] = -1;
+  const int last0 = seed_code[b];
+  if ((unsigned)last0 >= (unsigned)KB) {
+    if (lane == 0) status_out[b] = 1;
     return;
   }
-  Entry cur = load_entry(entries + q0 * KB + last);
-  __syncthreads();
+  float prev5[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) prev5[k] = seed_phase[(size_t)b * 8 * PC + (3 + k) * PC + hl];
+  Entry cur = load_entry(entries + q0 * KB + last0);
+  int status = 0;
+  __syncwarp();
   for (int st = 0; st < n_steps; ++st) {
     const int g = st >> 3, s = st & 7;
     const size_t q = q0 + st;
@@ -184,60 +250,158 @@ __global__ void __launch_bounds__(64)
       status |= 1;
       break;
     }
-    // both possible next entries (state independent addresses once `cur` is known)
-    Entry nx0 = cur, nx1 = cur;
+    Entry nx0 = cur, nx1 = cur;                      // both possible next entries, fetched while the pick is computed
     if (st + 1 < n_steps) {
       const int l0 = s == 7 ? cur.nls[0] : cur.nl[0], l1 = s == 7 ? cur.nls[1] : cur.nl[1];
       nx0 = load_entry(entries + (q + 1) * KB + l0);
       nx1 = load_entry(entries + (q + 1) * KB + l1);
     }
-    const long long w = warp == 0 ? cur.w[0] : cur.w[1];
+    const long long w = hw == 0 ? cur.w[0] : cur.w[1];
+    const long long j = w / WIN;
+    const int f = hw == 0 ? cur.frame[0] : cur.frame[1];
+    const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;      // rows f..f+7; rows f+24..f+31 = next prev
+    float tl[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) tl[k] = head[(24 + k) * PC + hl];
+    const int win = phase_pick(prev5, head, lane);
+    // the winner's tail rows become prev: lanes of the other half fetch them by shuffle
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float t = __shfl_sync(0xffffffffu, tl[k], win * 16 + hl);
+      if (k >= 3) prev5[k - 3] = t;
+      if (phase_out && hw == 0) phase_out[(q * 8 + k) * PC + hl] = t;
+    }
+    const long long ww = win == 0 ? cur.w[0] : cur.w[1];
+    const long long jw = ww / WIN;
+    const int mw = (int)(ww - jw * WIN);
+    if (lane < 4) {
+      const int p = s * 4 + lane;
+      if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = code[(size_t)jw * NCODE + mw + lane];
+    }
+    if (lane == 0) vote_out[q] = win;
+    cur = win == 0 ? nx0 : nx1;
+  }
+  if (lane == 0) status_out[b] = status;
+}
+
+// ---- transitions: the pick for EVERY reachable state, in parallel (few clips: nothing left on the chain) ----
+// state entering step st = (last, which) of the winner of step st-1, i.e. window entries[q-1][last].w[which]
+// (step 0: the seed, state 0).  trans[q][state] = next state | tie flag << 10;  -1 = IndexError at this step,
+// -2 = unreachable.  One warp per (step, state).
+__global__ void __launch_bounds__(256)
+    match_transition_kernel(const Entry* __restrict__ entries, const float* __restrict__ phase_amp,
+                            const int32_t* __restrict__ seed_code, const float* __restrict__ seed_phase, int n_steps,
+                            long long n_warps, int16_t* __restrict__ trans) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  if (wid >= n_warps) return;
+  const int lane = threadIdx.x & 31, hw = lane >> 4, hl = lane & 15;
+  const long long q = wid >> 10;
+  const int state = (int)(wid & 1023);
+  const int st = (int)(q % n_steps);
+  const long long b = q / n_steps;
+  int last;
+  float prev5[5];
+  if (st == 0) {
+    if (state != 0) {
+      if (lane == 0) trans[wid] = -2;
+      return;
+    }
+    last = seed_code[b];
+    if ((unsigned)last >= (unsigned)KB) {
+      if (lane == 0) trans[wid] = -1;
+      return;
+    }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) prev5[k] = seed_phase[(size_t)b * 8 * PC + (3 + k) * PC + hl];
+  } else {
+    const Entry ep = load_entry(entries + (q - 1) * KB + (state >> 1));
+    const int xp = state & 1;
+    const long long wp = xp == 0 ? ep.w[0] : ep.w[1];
+    if (ep.w[0] < 0 || ep.w[1] < 0) {                // the previous step raised: nothing continues from it
+      if (lane == 0) trans[wid] = -2;
+      return;
+    }
+    last = (st & 7) == 0 ? (xp == 0 ? ep.nls[0] : ep.nls[1]) : (xp == 0 ? ep.nl[0] : ep.nl[1]);
+    const long long jp = wp / WIN;
+    const int fp = xp == 0 ? ep.frame[0] : ep.frame[1];
+    const float* tailp = phase_amp + ((size_t)jp * NFRM + fp + 24) * PC;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) prev5[k] = tailp[(3 + k) * PC + hl];
+  }
+  const Entry e = load_entry(entries + q * KB + last);
+  if (e.w[0] < 0 || e.w[1] < 0) {
+    if (lane == 0) trans[wid] = -1;
+    return;
+  }
+  const long long w = hw == 0 ? e.w[0] : e.w[1];
+  const long long j = w / WIN;
+  const int f = hw == 0 ? e.frame[0] : e.frame[1];
+  const int win = phase_pick(prev5, phase_amp + ((size_t)j * NFRM + f) * PC, lane);
+  if (lane == 0) trans[wid] = (int16_t)((last << 1) | win | ((e.flags & 1) << 10));
+}
+
+// one CTA per clip: the clip's transition table goes to shared memory, one thread follows it, then all threads
+// write the outputs of the visited states
+constexpr int WALK_MAX_STEPS = 104;                  // 104 * 2 KiB = 208 KiB of shared memory
+__global__ void __launch_bounds__(256)
+    match_table_walk_kernel(const int16_t* __restrict__ trans, const Entry* __restrict__ entries,
+                            const int32_t* __restrict__ code, const float* __restrict__ phase_amp, int n_seg,
+                            int64_t* __restrict__ codes_out, int32_t* __restrict__ vote_out,
+                            float* __restrict__ phase_out, int32_t* __restrict__ status_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  int16_t* tab = reinterpret_cast<int16_t*>(smem_raw);                     // [n_steps][1024]
+  __shared__ int16_t s_state[WALK_MAX_STEPS];                              // (last << 1 | win) per visited step
+  __shared__ int s_done, s_status;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n_steps = n_seg * 8;
+  const size_t q0 = (size_t)b * n_steps;
+  {
+    const int4* src = reinterpret_cast<const int4*>(trans + q0 * 1024);
+    int4* dst = reinterpret_cast<int4*>(tab);
+    for (int i = tid; i < n_steps * 128; i += 256) dst[i] = __ldg(src + i);
+  }
+  for (int i = tid; i < n_seg * NCODE; i += 256) codes_out[(size_t)b * n_seg * NCODE + i] = -1;
+  __syncthreads();
+  if (tid == 0) {
+    int state = 0, status = 0, st = 0;
+    for (; st < n_steps; ++st) {
+      const int v = tab[st * 1024 + state];
+      if (v < 0) {
+        status |= 1;
+        break;
+      }
+      status |= (v >> 10) & 1 ? 2 : 0;
+      state = v & 1023;
+      s_state[st] = (int16_t)state;
+    }
+    s_done = st;
+    s_status = status;
+  }
+  __syncthreads();
+  const int done = s_done;
+  // outputs: 4 codes + vote + (optionally) the 8 x 16 phase block per visited step
+  for (int i = tid; i < done * 4; i += 256) {
+    const int st = i >> 2, k = i & 3, s = st & 7, g = st >> 3;
+    const int state = s_state[st];
+    const Entry e = load_entry(entries + (q0 + st) * KB + (state >> 1));
+    const long long w = (state & 1) == 0 ? e.w[0] : e.w[1];
     const long long j = w / WIN;
     const int m = (int)(w - j * WIN);
-    const int f = warp == 0 ? cur.frame[0] : cur.frame[1];
-    const float* head = phase_amp + ((size_t)j * NFRM + f) * PC;      // rows f..f+7; rows f+24..f+31 = next prev
-    float tl[4];
-    double av[4], bv[4], sa = 0.0, sb = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int e2 = lane + 32 * k, row = e2 >> 4, col = e2 & 15;
-      const float fa = row < 5 ? prev[(3 + row) * PC + col] : head[(row - 5) * PC + col];
-      const float fb = row < 3 ? prev[(5 + row) * PC + col] : head[(row - 3) * PC + col];
-      tl[k] = head[24 * PC + e2];
-      av[k] = (double)fa;
-      bv[k] = (double)fb;
-      sa = fma(av[k], av[k], sa);
-      sb = fma(bv[k], bv[k], sb);
-    }
-    sa = warp_sum(sa);
-    sb = warp_sum(sb);
-    const double na = sa > 0.0 ? sqrt(sa) : 1.0, nb = sb > 0.0 ? sqrt(sb) : 1.0;
-    double acc = 0.0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const double d = av[k] / na - bv[k] / nb;
-      acc = fma(d, d, acc);
-    }
-    const double dist = 0.5 * warp_sum(acc);
-    if (lane == 0) s_dist[warp] = dist;
-    bar64(1);
-    const int win = (s_dist[0] <= s_dist[1]) ? 0 : 1;                 // audio wins ties (:646)
-    if (warp == win) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        prev[lane + 32 * k] = tl[k];
-        if (phase_out) phase_out[(q * 8) * PC + lane + 32 * k] = tl[k];
-      }
-      if (lane < 4) {
-        const int p = s * 4 + lane;
-        if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = code[(size_t)j * NCODE + m + lane];
-      }
-      if (lane == 0) vote_out[q] = win;
-    }
-    cur = win == 0 ? nx0 : nx1;
-    bar64(2);
+    const int p = s * 4 + k;
+    if (p < NCODE) codes_out[((size_t)b * n_seg + g) * NCODE + p] = code[(size_t)j * NCODE + m + k];
+    if (k == 0) vote_out[q0 + st] = state & 1;
   }
-  if (threadIdx.x == 0) status_out[b] = status;
+  if (phase_out) {
+    for (int i = tid; i < done * 8 * PC; i += 256) {
+      const int st = i / (8 * PC), r = i - st * 8 * PC;
+      const int state = s_state[st];
+      const Entry e = load_entry(entries + (q0 + st) * KB + (state >> 1));
+      const long long w = (state & 1) == 0 ? e.w[0] : e.w[1];
+      const int f = (state & 1) == 0 ? e.frame[0] : e.frame[1];
+      phase_out[(q0 + st) * 8 * PC + r] = phase_amp[((size_t)(w / WIN) * NFRM + f + 24) * PC + r];
+    }
+  }
+  if (tid == 0) status_out[b] = s_status;
 }
 
 }  // namespace
@@ -255,7 +419,7 @@ extern "C" int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* t
                     txt_frame && entries,
                 "null pointer");
   QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(entries) & 15) == 0, "entries must be 16-byte aligned");
-  match_lookup_kernel<<<dim3((unsigned)Q, 4), 128, 0, (cudaStream_t)stream>>>(
+  match_lookup_kernel<<<dim3((unsigned)Q, 16), 256, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const Pair*>(aud_table), reinterpret_cast<const Pair*>(txt_table), aud_rank, txt_rank, pos_rank_t,
       freq_rank, code, n_seq, aud_frame, txt_frame, qflags_a, qflags_t, reinterpret_cast<Entry*>(entries));
   QPG_LAUNCH_CHECK();
@@ -264,15 +428,29 @@ extern "C" int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* t
 
 extern "C" int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp,
                               const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg,
-                              int64_t* codes_out, int32_t* vote_out, float* phase_out, int32_t* status_out,
-                              void* stream) {
+                              int16_t* trans, int64_t* codes_out, int32_t* vote_out, float* phase_out,
+                              int32_t* status_out, void* stream) {
   QPG_CHECK_ARG(n_clips >= 0 && n_seg >= 0, "negative size");
   if (n_clips == 0 || n_seg == 0) return QPG_OK;
   QPG_CHECK_ARG(entries && code && phase_amp && seed_code && seed_phase && codes_out && vote_out && status_out,
                 "null pointer");
-  match_walk_kernel<<<n_clips, 64, 0, (cudaStream_t)stream>>>(reinterpret_cast<const Entry*>(entries), code, phase_amp,
-                                                              seed_code, seed_phase, n_seg, codes_out, vote_out,
-                                                              phase_out, status_out);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n_steps = n_seg * 8;
+  if (trans != nullptr && n_steps <= WALK_MAX_STEPS) {
+    QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(trans) & 15) == 0, "trans must be 16-byte aligned");
+    const long long n_warps = (long long)n_clips * n_steps * 1024;
+    match_transition_kernel<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const Entry*>(entries), phase_amp, seed_code, seed_phase, n_steps, n_warps, trans);
+    QPG_LAUNCH_CHECK();
+    const size_t smem = (size_t)n_steps * 2048;
+    QPG_CUDA(cudaFuncSetAttribute(match_table_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    match_table_walk_kernel<<<n_clips, 256, smem, st>>>(trans, reinterpret_cast<const Entry*>(entries), code, phase_amp,
+                                                        n_seg, codes_out, vote_out, phase_out, status_out);
+    QPG_LAUNCH_CHECK();
+    return QPG_OK;
+  }
+  match_walk_kernel<<<n_clips, 32, 0, st>>>(reinterpret_cast<const Entry*>(entries), code, phase_amp, seed_code,
+                                            seed_phase, n_seg, codes_out, vote_out, phase_out, status_out);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

@@ -57,12 +57,29 @@ struct RowInfo {   // per sorted database row
 
 // One CTA per output row `pos`.  DB mode (n_rows_tile = 128): tile (pos/128, kb, s); query mode: one tile
 // column of n_pad rows, row = pos.  sign = -1 applies 2^-colexp (database), +1 applies 2^+colexp (queries).
+struct SliceJob {
+  const float* rows;
+  const int8_t* col_exp;
+  int8_t* out;
+  qpg_qinfo_t* q_info;
+  int64_t ld;
+  int D, nkb;
+};
+struct SliceJobs {
+  SliceJob j[2];
+};
+
 template <bool kQuery>
 __global__ void __launch_bounds__(128)
-    slice_kernel(const float* __restrict__ rows, int64_t n_rows, int D, int64_t ld, const int32_t* __restrict__ order,
-                 const int8_t* __restrict__ col_exp, int nkb, int n_pad, int8_t* __restrict__ out,
-                 const double* __restrict__ sqnorm_in, RowInfo* __restrict__ row_info,
-                 qpg_qinfo_t* __restrict__ q_info) {
+    slice_kernel(const SliceJobs jobs, const int32_t* __restrict__ order, int n_pad,
+                 const double* __restrict__ sqnorm_in, RowInfo* __restrict__ row_info) {
+  const SliceJob job = blockIdx.y == 0 ? jobs.j[0] : jobs.j[1];
+  const float* __restrict__ rows = job.rows;
+  const int8_t* __restrict__ col_exp = job.col_exp;
+  int8_t* __restrict__ out = job.out;
+  qpg_qinfo_t* __restrict__ q_info = job.q_info;
+  const int64_t ld = job.ld;
+  const int D = job.D, nkb = job.nkb;
   __shared__ double s_red[4];
   __shared__ unsigned long long s_l1[4], s_el[4];
   __shared__ int s_ex;
@@ -427,15 +444,36 @@ __device__ __forceinline__ double exact_distance(const float* __restrict__ packe
                                                  const float* __restrict__ q, int D, double sqq, double sqx, int lane) {
   const float* base = packed + (((size_t)(w >> 3) * NC) * 8 + (w & 7)) * 128;
   double acc = 0.0;
-  for (int c = 0; c < NC; ++c) {
+  // chunks that lie completely inside the D columns and can be read as float4 (row pointer 16-byte aligned)
+  const int full = (reinterpret_cast<uintptr_t>(q) & 15) == 0 ? D / 128 : 0;
+  int c = 0;
+  // eight chunks of loads in flight per round trip (the row is read once, from HBM): the FMA order is the
+  // plain ascending one, so the result does not depend on the unrolling
+  for (; c + 8 <= full; c += 8) {
+    float4 xv[8], qv[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      xv[u] = __ldg(reinterpret_cast<const float4*>(base + (size_t)(c + u) * 1024 + 4 * lane));
+      qv[u] = __ldg(reinterpret_cast<const float4*>(q + (c + u) * 128 + 4 * lane));
+    }
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      acc = fma((double)xv[u].x, (double)qv[u].x, acc);
+      acc = fma((double)xv[u].y, (double)qv[u].y, acc);
+      acc = fma((double)xv[u].z, (double)qv[u].z, acc);
+      acc = fma((double)xv[u].w, (double)qv[u].w, acc);
+    }
+  }
+  for (; c < NC; ++c) {
     const float4 xv = *reinterpret_cast<const float4*>(base + (size_t)c * 1024 + 4 * lane);
     const int k = c * 128 + 4 * lane;
     float4 qv = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (k + 3 < D) qv = *reinterpret_cast<const float4*>(q + k);
+    if (c < full) qv = *reinterpret_cast<const float4*>(q + k);
     else {
       if (k < D) qv.x = q[k];
       if (k + 1 < D) qv.y = q[k + 1];
       if (k + 2 < D) qv.z = q[k + 2];
+      if (k + 3 < D) qv.w = q[k + 3];
     }
     acc = fma((double)xv.x, (double)qv.x, acc);
     acc = fma((double)xv.y, (double)qv.y, acc);
@@ -445,9 +483,9 @@ __device__ __forceinline__ double exact_distance(const float* __restrict__ packe
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   const double a = sqq > kTinySq ? 1.0 : 0.0, b = sqx > kTinySq ? 1.0 : 0.0;
-  double c = 0.0;
-  if (sqq > kTinySq && sqx > kTinySq) c = acc / (sqrt(sqq) * sqrt(sqx));
-  const double d = 0.5 * (a + b) - c;
+  double cs = 0.0;
+  if (sqq > kTinySq && sqx > kTinySq) cs = acc / (sqrt(sqq) * sqrt(sqx));
+  const double d = 0.5 * (a + b) - cs;
   return d < 0.0 ? 0.0 : d;
 }
 
@@ -469,23 +507,42 @@ __device__ __forceinline__ Interval filter_interval(long long v, const RowInfo r
 }
 
 // ------------------------------------------------------------------ per-bin records
-// One warp per (query, start code): U = min hi over the bin's rows; candidates = rows whose interval reaches
-// below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly those rows
-// (lexicographic (d, id) minimum) -> exact record lo = hi = d.
+struct TableParams {         // device copy of qpg_sliced_table_t
+  const float* packed;
+  const double* sqnorm;
+  const float* q;
+  const qpg_qinfo_t* q_info;
+  long long ldq;
+  int D, NC;
+  long long* sacc;
+  const int32_t* bin_start;
+  const RowInfo* row_info;
+  const int32_t* order;
+  qpg_bin_t* bins;
+  Pair* table;
+  int32_t* ranks;
+  int32_t* qflags;
+};
+struct TablePair {
+  TableParams t[2];
+};
+
+// One warp per (table, query, start code): U = min hi over the bin's rows; candidates = rows whose interval
+// reaches below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly those
+// rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  With `consume` the entries of sacc are
+// zeroed once read, so the next pass needs no memset.
 __global__ void __launch_bounds__(256)
-    sliced_bins_kernel(const long long* __restrict__ sacc, long long Wpad, int nq, const int32_t* __restrict__ bin_start,
-                       const RowInfo* __restrict__ row_info, const int32_t* __restrict__ order,
-                       const double* __restrict__ sqnorm, int64_t id_offset, int64_t row_base,
-                       const qpg_qinfo_t* __restrict__ q_info, const float* __restrict__ packed, int NC, int D,
-                       const float* __restrict__ q, int64_t ldq, qpg_bin_t* __restrict__ out,
+    sliced_bins_kernel(const TablePair tp, long long Wpad, int nq, int64_t id_offset, int64_t row_base, int consume,
                        unsigned long long* __restrict__ stats) {
+  const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
   if (wid >= (long long)nq * KB) return;
   const int qi_ = (int)(wid / KB), c = (int)(wid % KB);
-  const qpg_qinfo_t qi = q_info[qi_];
-  const int b0 = bin_start[c], b1 = bin_start[c + 1];
-  const long long* sv = sacc + (size_t)qi_ * Wpad;
+  const qpg_qinfo_t qi = T.q_info[qi_];
+  const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
+  long long* sv = T.sacc + (size_t)qi_ * Wpad;
+  const float* qrow = T.q + (size_t)qi_ * T.ldq;
   qpg_bin_t rec;
   rec.lo = kEmptyDist;
   rec.hi = kEmptyDist;
@@ -495,7 +552,7 @@ __global__ void __launch_bounds__(256)
   if (b1 > b0) {
     double U = 1e300;
     for (int pos = b0 + lane; pos < b1; pos += 32) {
-      const Interval iv = filter_interval(sv[pos], row_info[pos], qi);
+      const Interval iv = filter_interval(sv[pos], T.row_info[pos], qi);
       U = fmin(U, iv.hi);
     }
 #pragma unroll
@@ -508,8 +565,9 @@ __global__ void __launch_bounds__(256)
       bool cand = false;
       Interval iv{0.0, 0.0};
       if (pos < b1) {
-        iv = filter_interval(sv[pos], row_info[pos], qi);
+        iv = filter_interval(sv[pos], T.row_info[pos], qi);
         cand = iv.lo <= U;
+        if (consume) sv[pos] = 0;
       }
       const unsigned m = __ballot_sync(0xffffffffu, cand);
       const int cnt = __popc(m);
@@ -523,8 +581,8 @@ __global__ void __launch_bounds__(256)
       }
       // more than one candidate so far: evaluate exactly (including the remembered one)
       if (n == 1 && single_pos >= 0) {
-        const long long w = order[single_pos];
-        const double d = exact_distance(packed, NC, w + row_base, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w + row_base], lane);
+        const long long w = T.order[single_pos];
+        const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, qi.sq, T.sqnorm[w + row_base], lane);
         best_d = d;
         best_id = id_offset + w;
         single_pos = -1;
@@ -533,8 +591,8 @@ __global__ void __launch_bounds__(256)
       while (mm) {
         const int src_lane = __ffs(mm) - 1;
         mm &= mm - 1;
-        const long long w = order[base + src_lane];
-        const double d = exact_distance(packed, NC, w + row_base, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w + row_base], lane);
+        const long long w = T.order[base + src_lane];
+        const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, qi.sq, T.sqnorm[w + row_base], lane);
         const long long id = id_offset + w;
         if (d < best_d || (d == best_d && id < best_id)) {
           best_d = d;
@@ -546,39 +604,39 @@ __global__ void __launch_bounds__(256)
     if (n == 1 && single_pos >= 0) {
       rec.lo = best_lo;
       rec.hi = U;
-      rec.id = id_offset + order[single_pos];
+      rec.id = id_offset + T.order[single_pos];
       rec.n = 1;
     } else {
       rec.lo = best_d;
       rec.hi = best_d;
       rec.id = best_id;
-      rec.n = 1;
+      rec.n = n;                             // how many rows were re-evaluated (diagnostics)
       rec.flags = 1;                         // exact
       if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
     }
   } else {
     rec.flags = 1;                           // empty bins are exact (sentinel)
   }
-  if (lane == 0) out[(size_t)qi_ * KB + c] = rec;
+  if (lane == 0) T.bins[(size_t)qi_ * KB + c] = rec;
 }
 
 // ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
-// One CTA (512 threads, thread = start code) per query.  parts [P][nq][512] (P = 1 on a single GPU, the
-// all-gathered per-rank records when database rows are sharded).  `packed`/`sqnorm` address rows by GLOBAL
-// window id - first_id (a replicated float32 copy of the whole table), so any rank can re-evaluate any
-// candidate.  Output: table [nq][512] (distance exact where it had to be decided, else the filter value),
-// ranks [nq][512] (stable, as qpg_rank512), qflags [nq] bit0 = exact tie between two non-empty bins.
+// One CTA (512 threads, thread = start code) per (table, query).  T.bins points at part 0; part p is
+// part_stride records further (P = 1 on a single GPU, the all-gathered per-rank records when database rows are
+// sharded).  T.packed / T.sqnorm address rows by GLOBAL window id - first_id (a replicated float32 copy of the
+// whole table), so any rank can re-evaluate any candidate.  Output: table [nq][512] (distance exact where it had
+// to be decided, else the centre of the filter interval), ranks [nq][512] (stable, as qpg_rank512),
+// qflags [nq] bit 0 = exact tie between two non-empty bins.
 __global__ void __launch_bounds__(KB)
-    sliced_resolve_kernel(const qpg_bin_t* __restrict__ parts, int P, long long part_stride, const float* __restrict__ packed, int NC,
-                          int D, const double* __restrict__ sqnorm, int64_t first_id,
-                          const qpg_qinfo_t* __restrict__ q_info, const float* __restrict__ q, int64_t ldq,
-                          Pair* __restrict__ table, int32_t* __restrict__ ranks, int32_t* __restrict__ qflags,
+    sliced_resolve_kernel(const TablePair tp, int P, long long part_stride, int64_t first_id,
                           unsigned long long* __restrict__ stats) {
   __shared__ double s_lo[KB], s_hi[KB];
   __shared__ unsigned long long s_d[KB];
   __shared__ long long s_id[KB];
   __shared__ int s_list[KB];
   __shared__ int s_n, s_tie;
+  const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
+  const qpg_bin_t* __restrict__ parts = T.bins;
   const int qi_ = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
   if (c == 0) {
     s_n = 0;
@@ -609,20 +667,19 @@ __global__ void __launch_bounds__(KB)
     }
   }
   if (ncand > 0) hi = U;
-  if (ncand == 1 && exact) lo = hi;             // an exact record is a point (hi == lo already)
   s_lo[c] = lo;
   s_hi[c] = hi;
   __syncthreads();
+  // a bin needs a float64 decision when several shards could hold its winner, or when its interval overlaps
+  // another bin's (the rank transform would be undecided); exact points need nothing
   bool need = ncand > 1;
-  if (ncand >= 1 && !need && !(exact && lo == hi)) {
+  if (ncand == 1 && !(exact && lo == hi)) {
     for (int j = 0; j < KB; ++j) {
       if (j != c && s_lo[j] <= hi && lo <= s_hi[j] && s_hi[j] < kEmptyDist) {
         need = true;
         break;
       }
     }
-  } else if (ncand == 1 && exact) {
-    // a point still needs nothing; intervals that contain it are flagged by their own thread
   }
   if (need) s_list[atomicAdd(&s_n, 1)] = c;
   __syncthreads();
@@ -630,10 +687,11 @@ __global__ void __launch_bounds__(KB)
   s_id[c] = id;
   s_d[c] = (unsigned long long)__double_as_longlong(ncand >= 1 ? 0.5 * (lo + hi) : kEmptyDist);
   __syncthreads();
-  const qpg_qinfo_t qi = q_info[qi_];
+  const qpg_qinfo_t qi = T.q_info[qi_];
+  const float* qrow = T.q + (size_t)qi_ * T.ldq;
   for (int it = warp; it < n_list; it += KB / 32) {
     const int cc = s_list[it];
-    double Uc = s_hi[cc];
+    const double Uc = s_hi[cc];
     double bd = 1e300;
     long long bid = -1;
     for (int p = 0; p < P; ++p) {
@@ -643,7 +701,7 @@ __global__ void __launch_bounds__(KB)
         if (r.flags & 1) d = r.lo;
         else {
           const int64_t w = r.id - first_id;
-          d = exact_distance(packed, NC, w, q + (size_t)qi_ * ldq, D, qi.sq, sqnorm[w], lane);
+          d = exact_distance(T.packed, T.NC, w, qrow, T.D, qi.sq, T.sqnorm[w], lane);
         }
         if (d < bd || (d == bd && r.id < bid)) {
           bd = d;
@@ -672,10 +730,10 @@ __global__ void __launch_bounds__(KB)
   Pair out;
   out.d = mine;
   out.id = (unsigned long long)s_id[c];
-  table[(size_t)qi_ * KB + c] = out;
-  ranks[(size_t)qi_ * KB + c] = r;
+  T.table[(size_t)qi_ * KB + c] = out;
+  T.ranks[(size_t)qi_ * KB + c] = r;
   __syncthreads();
-  if (c == 0 && qflags) qflags[qi_] = s_tie;
+  if (c == 0 && T.qflags) T.qflags[qi_] = s_tie;
 }
 
 }  // namespace
@@ -702,25 +760,44 @@ extern "C" int qpg_slice_rows_i8(const float* rows, int64_t W, int D, const int3
   QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(slices) & 1023) == 0, "slices must be 1024-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
   QPG_CUDA(cudaMemsetAsync(slices, 0, qpg_sliced_bytes(W, D), st));
-  const int nkb = (D + KBW - 1) / KBW;
-  slice_kernel<false><<<(unsigned)W, 128, 0, st>>>(rows, W, D, D, order, col_exp, nkb, 0, slices, row_sqnorm,
-                                                   reinterpret_cast<RowInfo*>(row_info), nullptr);
+  SliceJobs jobs;
+  jobs.j[0].rows = rows;
+  jobs.j[0].col_exp = col_exp;
+  jobs.j[0].out = slices;
+  jobs.j[0].q_info = nullptr;
+  jobs.j[0].ld = D;
+  jobs.j[0].D = D;
+  jobs.j[0].nkb = (D + KBW - 1) / KBW;
+  jobs.j[1] = jobs.j[0];
+  slice_kernel<false><<<dim3((unsigned)W, 1), 128, 0, st>>>(jobs, order, 0, row_sqnorm,
+                                                           reinterpret_cast<RowInfo*>(row_info));
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
 
-extern "C" int qpg_slice_queries_i8(const float* q, int Q, int D, int64_t ldq, const int8_t* col_exp, int n_pad,
-                                    int8_t* q_slices, qpg_qinfo_t* q_info, void* stream) {
-  QPG_CHECK_ARG(Q >= 0 && D > 0 && D <= 32768 && ldq >= D, "Q >= 0, 0 < D <= 32768, ldq >= D");
-  QPG_CHECK_ARG(n_pad >= 16 && n_pad <= MAX_NPAD && n_pad % 16 == 0 && Q <= n_pad, "n_pad in {16,32,48,64}, Q <= n_pad");
+extern "C" int qpg_slice_queries_i8(const qpg_slice_job_t* jobs_in, int n_jobs, int Q, int n_pad, void* stream) {
+  QPG_CHECK_ARG(jobs_in && (n_jobs == 1 || n_jobs == 2), "1 or 2 feature blocks");
+  QPG_CHECK_ARG(Q >= 0 && n_pad >= 16 && n_pad <= MAX_NPAD && n_pad % 16 == 0 && Q <= n_pad,
+                "n_pad in {16,32,48,64}, Q <= n_pad");
   if (Q == 0) return QPG_OK;
-  QPG_CHECK_ARG(q && q_slices && q_info, "null pointer");
-  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(q_slices) & 1023) == 0, "q_slices must be 1024-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (Q < n_pad || D % KBW != 0) QPG_CUDA(cudaMemsetAsync(q_slices, 0, qpg_sliced_query_bytes(D, n_pad), st));
-  const int nkb = (D + KBW - 1) / KBW;
-  slice_kernel<true><<<(unsigned)Q, 128, 0, st>>>(q, Q, D, ldq, nullptr, col_exp, nkb, n_pad, q_slices, nullptr, nullptr,
-                                                  q_info);
+  SliceJobs jobs;
+  for (int i = 0; i < n_jobs; ++i) {
+    const qpg_slice_job_t& j = jobs_in[i];
+    QPG_CHECK_ARG(j.D > 0 && j.D <= 32768 && j.ldq >= j.D, "0 < D <= 32768, ldq >= D");
+    QPG_CHECK_ARG(j.q && j.q_slices && j.q_info, "null pointer");
+    QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(j.q_slices) & 1023) == 0, "q_slices must be 1024-byte aligned");
+    if (Q < n_pad || j.D % KBW != 0) QPG_CUDA(cudaMemsetAsync(j.q_slices, 0, qpg_sliced_query_bytes(j.D, n_pad), st));
+    jobs.j[i].rows = j.q;
+    jobs.j[i].col_exp = j.col_exp;
+    jobs.j[i].out = j.q_slices;
+    jobs.j[i].q_info = j.q_info;
+    jobs.j[i].ld = j.ldq;
+    jobs.j[i].D = j.D;
+    jobs.j[i].nkb = (j.D + KBW - 1) / KBW;
+  }
+  if (n_jobs == 1) jobs.j[1] = jobs.j[0];
+  slice_kernel<true><<<dim3((unsigned)Q, (unsigned)n_jobs), 128, 0, st>>>(jobs, nullptr, n_pad, nullptr, nullptr);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
@@ -778,36 +855,61 @@ extern "C" int qpg_sliced_scan_ref(const int8_t* db_slices, const int8_t* q_slic
   return QPG_OK;
 }
 
-extern "C" int qpg_sliced_bins(const int64_t* sacc, int64_t W, int nq, const int32_t* bin_start, const void* row_info,
-                               const int32_t* order, const double* row_sqnorm, int64_t id_offset, int64_t row_base,
-                               const qpg_qinfo_t* q_info, const float* packed, int D, const float* q, int64_t ldq,
-                               qpg_bin_t* bins_out, uint64_t* stats, void* stream) {
-  QPG_CHECK_ARG(W >= 0 && nq >= 0 && D > 0 && ldq >= D, "bad size");
+static int fill_tables(const qpg_sliced_table_t* tabs, int n_tabs, bool for_bins, TablePair* tp) {
+  QPG_CHECK_ARG(tabs && (n_tabs == 1 || n_tabs == 2), "1 or 2 tables");
+  for (int i = 0; i < n_tabs; ++i) {
+    const qpg_sliced_table_t& t = tabs[i];
+    QPG_CHECK_ARG(t.D > 0 && t.ldq >= t.D, "D > 0, ldq >= D");
+    QPG_CHECK_ARG(t.packed && t.row_sqnorm && t.q && t.q_info && t.bins, "null pointer");
+    if (for_bins) QPG_CHECK_ARG(t.sacc && t.bin_start && t.row_info && t.order, "null pointer (bins inputs)");
+    else QPG_CHECK_ARG(t.table && t.ranks, "null pointer (resolve outputs)");
+    TableParams& o = tp->t[i];
+    o.packed = t.packed;
+    o.sqnorm = t.row_sqnorm;
+    o.q = t.q;
+    o.q_info = t.q_info;
+    o.ldq = t.ldq;
+    o.D = t.D;
+    o.NC = (t.D + 127) / 128;
+    o.sacc = reinterpret_cast<long long*>(t.sacc);
+    o.bin_start = t.bin_start;
+    o.row_info = reinterpret_cast<const RowInfo*>(t.row_info);
+    o.order = t.order;
+    o.bins = t.bins;
+    o.table = reinterpret_cast<Pair*>(t.table);
+    o.ranks = t.ranks;
+    o.qflags = t.qflags;
+  }
+  if (n_tabs == 1) tp->t[1] = tp->t[0];
+  return QPG_OK;
+}
+
+extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64_t W, int nq, int64_t id_offset,
+                               int64_t row_base, int consume, uint64_t* stats, void* stream) {
+  QPG_CHECK_ARG(W >= 0 && nq >= 0, "bad size");
   if (nq == 0) return QPG_OK;
-  QPG_CHECK_ARG(sacc && bin_start && row_info && order && row_sqnorm && q_info && packed && q && bins_out,
-                "null pointer");
+  TablePair tp;
+  const int rc = fill_tables(tabs, n_tabs, true, &tp);
+  if (rc != QPG_OK) return rc;
   const long long Wpad = (W + TM - 1) / TM * TM;
   const long long warps = (long long)nq * KB;
-  const unsigned blocks = (unsigned)((warps * 32 + 255) / 256);
-  sliced_bins_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(
-      reinterpret_cast<const long long*>(sacc), Wpad, nq, bin_start, reinterpret_cast<const RowInfo*>(row_info), order,
-      row_sqnorm, id_offset, row_base, q_info, packed, (D + 127) / 128, D, q, ldq, bins_out,
-      reinterpret_cast<unsigned long long*>(stats));
+  const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);
+  sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, Wpad, nq, id_offset, row_base, consume,
+                                                             reinterpret_cast<unsigned long long*>(stats));
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
 
-extern "C" int qpg_sliced_resolve(const qpg_bin_t* parts, int n_parts, int64_t part_stride, int nq, const float* packed, int D,
-                                  const double* row_sqnorm, int64_t first_id, const qpg_qinfo_t* q_info, const float* q,
-                                  int64_t ldq, qpg_pair_t* table, int32_t* ranks, int32_t* qflags, uint64_t* stats,
-                                  void* stream) {
-  QPG_CHECK_ARG(n_parts >= 1 && nq >= 0 && D > 0 && ldq >= D, "bad size");
+extern "C" int qpg_sliced_resolve(const qpg_sliced_table_t* tabs, int n_tabs, int n_parts, int64_t part_stride, int nq,
+                                  int64_t first_id, uint64_t* stats, void* stream) {
+  QPG_CHECK_ARG(n_parts >= 1 && nq >= 0, "bad size");
   QPG_CHECK_ARG(n_parts == 1 || part_stride >= (int64_t)nq * KB, "part_stride smaller than one part");
   if (nq == 0) return QPG_OK;
-  QPG_CHECK_ARG(parts && packed && row_sqnorm && q_info && q && table && ranks, "null pointer");
-  sliced_resolve_kernel<<<nq, KB, 0, (cudaStream_t)stream>>>(parts, n_parts, (long long)part_stride, packed, (D + 127) / 128, D, row_sqnorm,
-                                                             first_id, q_info, q, ldq, reinterpret_cast<Pair*>(table),
-                                                             ranks, qflags, reinterpret_cast<unsigned long long*>(stats));
+  TablePair tp;
+  const int rc = fill_tables(tabs, n_tabs, false, &tp);
+  if (rc != QPG_OK) return rc;
+  sliced_resolve_kernel<<<dim3((unsigned)nq, (unsigned)n_tabs), KB, 0, (cudaStream_t)stream>>>(
+      tp, n_parts, (long long)part_stride, first_id, reinterpret_cast<unsigned long long*>(stats));
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

@@ -35,9 +35,23 @@ def _slice_queries(q_d, col_exp, n_pad):
     Q, D = q_d.shape
     qs = aligned_bytes(lib.qpg_sliced_query_bytes(D, n_pad), dev)
     qinfo = torch.zeros((Q, 4), dtype=torch.float64, device=dev)
-    _lib.check(lib.qpg_slice_queries_i8(_lib.ptr(q_d), Q, D, D, _lib.ptr(col_exp), n_pad, _lib.ptr(qs), _lib.ptr(qinfo),
-                                        _lib.stream_ptr()), "slice_q")
+    job = (_lib.SliceJob * 1)()
+    job[0].q, job[0].col_exp, job[0].q_slices, job[0].q_info = _lib.dptr(q_d), _lib.dptr(col_exp), _lib.dptr(qs), _lib.dptr(qinfo)
+    job[0].ldq, job[0].D = D, D
+    _lib.check(lib.qpg_slice_queries_i8(job, 1, Q, n_pad, _lib.stream_ptr()), "slice_q")
+    torch.cuda.synchronize()
     return qs, qinfo
+
+
+def _table_desc(pr, S, q_d, qinfo, sacc=None, bins=None, tab=None, ranks=None, qf=None):
+    torch, _lib, lib, dev = _env()
+    t = (_lib.SlicedTable * 1)()
+    t[0].packed, t[0].row_sqnorm, t[0].q, t[0].q_info = _lib.dptr(pr.packed), _lib.dptr(pr.sqnorm), _lib.dptr(q_d), _lib.dptr(qinfo)
+    t[0].ldq, t[0].D = q_d.shape[1], q_d.shape[1]
+    if S is not None:
+        t[0].sacc, t[0].bin_start, t[0].row_info, t[0].order = _lib.dptr(sacc), _lib.dptr(S.bin_start), _lib.dptr(S.row_info), _lib.dptr(S.order)
+    t[0].bins, t[0].table, t[0].ranks, t[0].qflags = _lib.dptr(bins), _lib.dptr(tab), _lib.dptr(ranks), _lib.dptr(qf)
+    return t
 
 
 def _scan_tc(segs_spec, W, n_pad, nq):
@@ -185,16 +199,14 @@ def _tables_sliced(rows, labels, q, id_offset=0, column_scaling=True):
     bins = torch.zeros((Q, 512, 4), dtype=torch.int64, device=dev)
     stats = torch.zeros((2,), dtype=torch.int64, device=dev)
     sp = _lib.stream_ptr()
-    _lib.check(lib.qpg_sliced_bins(_lib.ptr(sacc), W, Q, _lib.ptr(S.bin_start), _lib.ptr(S.row_info), _lib.ptr(S.order),
-                                   _lib.ptr(pr.sqnorm), id_offset, 0, _lib.ptr(qinfo), _lib.ptr(pr.packed), D,
-                                   _lib.ptr(q_d), D, _lib.ptr(bins), _lib.ptr(stats), sp), "bins")
     tab = new_table(Q, dev)
     ranks = torch.zeros((Q, 512), dtype=torch.int32, device=dev)
     qf = torch.zeros((Q,), dtype=torch.int32, device=dev)
-    _lib.check(lib.qpg_sliced_resolve(_lib.ptr(bins), 1, Q * 512, Q, _lib.ptr(pr.packed), D, _lib.ptr(pr.sqnorm), id_offset,
-                                      _lib.ptr(qinfo), _lib.ptr(q_d), D, _lib.ptr(tab), _lib.ptr(ranks), _lib.ptr(qf),
-                                      _lib.ptr(stats), sp), "resolve")
+    desc = _table_desc(pr, S, q_d, qinfo, sacc, bins, tab, ranks, qf)
+    _lib.check(lib.qpg_sliced_bins(desc, 1, W, Q, id_offset, 0, 1, _lib.ptr(stats), sp), "bins")
+    _lib.check(lib.qpg_sliced_resolve(desc, 1, 1, Q * 512, Q, id_offset, _lib.ptr(stats), sp), "resolve")
     torch.cuda.synchronize()
+    assert not bool(sacc[:, :W].any()), "consume=1 must leave sacc zeroed for the next pass"
     return table_to_numpy(tab), ranks.cpu().numpy(), qf.cpu().numpy(), stats.cpu().numpy(), bins
 
 
@@ -297,9 +309,8 @@ def test_resolve_merges_row_shards():
     tab = new_table(Q, dev)
     ranks = torch.zeros((Q, 512), dtype=torch.int32, device=dev)
     qf = torch.zeros((Q,), dtype=torch.int32, device=dev)
-    _lib.check(lib.qpg_sliced_resolve(_lib.ptr(parts_d), 3, Q * 512, Q, _lib.ptr(pr.packed), D, _lib.ptr(pr.sqnorm), 0,
-                                      _lib.ptr(qinfo), _lib.ptr(q_d), D, _lib.ptr(tab), _lib.ptr(ranks), _lib.ptr(qf), None,
-                                      _lib.stream_ptr()), "resolve")
+    desc = _table_desc(pr, None, q_d, qinfo, None, parts_d, tab, ranks, qf)
+    _lib.check(lib.qpg_sliced_resolve(desc, 1, 3, Q * 512, Q, 0, None, _lib.stream_ptr()), "resolve")
     torch.cuda.synchronize()
     merged = table_to_numpy(tab)
     assert np.array_equal(merged["id"], full["id"])
@@ -345,7 +356,7 @@ def test_lookup_walk_equals_round1_tail():
     _lib.check(lib.qpg_rank512_ties(_lib.ptr(ta_d), Q, _lib.ptr(ra), _lib.ptr(qfa), sp), "rank")
     _lib.check(lib.qpg_rank512_ties(_lib.ptr(tt_d), Q, _lib.ptr(rt), _lib.ptr(qft), sp), "rank")
     outs = []
-    for which in ("old", "new"):
+    for which in ("old", "direct", "table"):
         codes = torch.full((n_clips, n_seg, 30), -7, dtype=torch.int64, device=dev)
         vote = torch.zeros((n_clips, n_seg, 8), dtype=torch.int32, device=dev)
         status = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
@@ -360,12 +371,19 @@ def test_lookup_walk_equals_round1_tail():
             _lib.check(lib.qpg_match_lookup(_lib.ptr(ta_d), _lib.ptr(tt_d), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(pos_t_d),
                                             _lib.ptr(freq_d), _lib.ptr(code_d), n_seq, _lib.ptr(fa_d), _lib.ptr(ft_d),
                                             _lib.ptr(qfa), _lib.ptr(qft), Q, _lib.ptr(entries), sp), "lookup")
+            trans = torch.empty((Q, 1024), dtype=torch.int16, device=dev) if which == "table" else None
             _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(code_d), _lib.ptr(phase_d), _lib.ptr(sc_d),
-                                          _lib.ptr(sp_d), n_clips, n_seg, _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(ph),
-                                          _lib.ptr(status), sp), "walk")
+                                          _lib.ptr(sp_d), n_clips, n_seg, _lib.ptr(trans), _lib.ptr(codes), _lib.ptr(vote),
+                                          _lib.ptr(ph), _lib.ptr(status), sp), "walk")
         torch.cuda.synchronize()
         outs.append((codes.cpu().numpy(), vote.cpu().numpy(), status.cpu().numpy(), ph.cpu().numpy()))
-    (c0, v0, s0, p0), (c1, v1, s1, p1) = outs
+    (c0, v0, s0, p0), (c1, v1, s1, p1), (c2, v2, s2, p2) = outs
+    # direct walk and table walk are the same arithmetic: bit-identical, failed clip included
+    assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
+    for b in range(n_clips):
+        done = n_seg * 8 if b != 3 else 5
+        assert np.array_equal(v1[b].ravel()[:done], v2[b].ravel()[:done])
+        assert np.array_equal(p1[b].reshape(-1, 8, 16)[:done], p2[b].reshape(-1, 8, 16)[:done])
     assert s0[3] == 1 and (s1[3] & 1) == 1
     ok = [b for b in range(n_clips) if b != 3]
     assert np.all((s1[ok] & 1) == 0) and np.all(s0[ok] == 0)
@@ -389,6 +407,9 @@ def test_tie_flags():
     frames = np.array([int(6 * m / 398 * 240) for m in range(26)], dtype=np.int32)
     to = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
 
+    pos_t_d, freq_d, code_d, frames_d, phase_d = to(pos_rank.T.astype(np.int16)), to(freq_rank), to(code), to(frames), to(phase)
+    sc_d, sp_d = to(np.array([5], dtype=np.int32)), to(rng.standard_normal((1, 8, 16)).astype(np.float32))
+
     def run(ta, tt):
         Q = 8
         ta_d, tt_d = to(ta.view(np.int64).reshape(Q, 512, 2)), to(tt.view(np.int64).reshape(Q, 512, 2))
@@ -403,14 +424,13 @@ def test_tie_flags():
         codes = torch.zeros((1, 1, 30), dtype=torch.int64, device=dev)
         vote = torch.zeros((1, 1, 8), dtype=torch.int32, device=dev)
         status = torch.zeros((1,), dtype=torch.int32, device=dev)
-        _lib.check(lib.qpg_match_lookup(_lib.ptr(ta_d), _lib.ptr(tt_d), _lib.ptr(ra), _lib.ptr(rt),
-                                        _lib.ptr(to(pos_rank.T.astype(np.int16))), _lib.ptr(to(freq_rank)),
-                                        _lib.ptr(to(code)), n_seq, _lib.ptr(to(frames)), _lib.ptr(to(frames)),
+        _lib.check(lib.qpg_match_lookup(_lib.ptr(ta_d), _lib.ptr(tt_d), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(pos_t_d),
+                                        _lib.ptr(freq_d), _lib.ptr(code_d), n_seq, _lib.ptr(frames_d), _lib.ptr(frames_d),
                                         _lib.ptr(qfa), _lib.ptr(qft), Q, _lib.ptr(entries), sp), "lookup")
-        _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(to(code)), _lib.ptr(to(phase)),
-                                      _lib.ptr(to(np.array([5], dtype=np.int32))),
-                                      _lib.ptr(to(rng.standard_normal((1, 8, 16)).astype(np.float32))), 1, 1,
-                                      _lib.ptr(codes), _lib.ptr(vote), None, _lib.ptr(status), sp), "walk")
+        trans = torch.empty((Q, 1024), dtype=torch.int16, device=dev)
+        _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(code_d), _lib.ptr(phase_d), _lib.ptr(sc_d),
+                                      _lib.ptr(sp_d), 1, 1, _lib.ptr(trans), _lib.ptr(codes), _lib.ptr(vote), None,
+                                      _lib.ptr(status), sp), "walk")
         torch.cuda.synchronize()
         return int(status.cpu()[0])
 

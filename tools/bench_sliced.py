@@ -75,48 +75,60 @@ def main():
         sp = _lib.stream_ptr()
         A, T = db.aud_s, db.txt_s
         ps = p.passes[0]
-        qa, qt = p.qa[ps.q0:ps.q0 + ps.nq], p.qt[ps.q0:ps.q0 + ps.nq]
-        qia, qit = p.qinfo_a[ps.q0:ps.q0 + ps.nq], p.qinfo_t[ps.q0:ps.q0 + ps.nq]
-
-        def slice_q():
-            lib.qpg_slice_queries_i8(_lib.ptr(qa), ps.nq, A.D, A.D, _lib.ptr(A.col_exp), ps.n_pad, _lib.ptr(ps.qs_a), _lib.ptr(qia), sp)
-            lib.qpg_slice_queries_i8(_lib.ptr(qt), ps.nq, T.D, T.D, _lib.ptr(T.col_exp), ps.n_pad, _lib.ptr(ps.qs_t), _lib.ptr(qit), sp)
+        jobs = (_lib.SliceJob * 2)()
+        for x, (S, q, qi, qs) in enumerate(((A, p.qa, p.qinfo_a, ps.qs_a), (T, p.qt, p.qinfo_t, ps.qs_t))):
+            jobs[x].q, jobs[x].col_exp = _lib.dptr(q[ps.q0:ps.q0 + ps.nq]), _lib.dptr(S.col_exp)
+            jobs[x].q_slices, jobs[x].q_info = _lib.dptr(qs), _lib.dptr(qi[ps.q0:ps.q0 + ps.nq])
+            jobs[x].ldq, jobs[x].D = S.D, S.D
         segs = (_lib.SlicedSeg * 2)()
         segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.data_ptr(), ps.qs_a.data_ptr(), p.sacc_a.data_ptr(), A.n_kblocks
         segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
+        tabs_b = knn._sliced_tables(p, ps.q0, ps.nq, ps.q0)
+        tabs_r = knn._sliced_tables(p, 0, p.Qt, 0, for_resolve=True)
 
-        def zero():
-            p.sacc_a.zero_()
-            p.sacc_t.zero_()
+        def slice_q():
+            lib.qpg_slice_queries_i8(jobs, 2, ps.nq, ps.n_pad, sp)
 
-        def scan():
+        def scan():            # accumulates on top of earlier repetitions: timing only
             lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp)
 
         def scan_audio_only():
             lib.qpg_sliced_scan_i8(segs, 1, A.W, ps.n_pad, ps.nq, sp)
 
-        def bins():
-            for x, (S, E, sacc, q, qi) in enumerate(((A, db.aud, p.sacc_a, qa, qia), (T, db.txt, p.sacc_t, qt, qit))):
-                lib.qpg_sliced_bins(_lib.ptr(sacc), S.W, ps.nq, _lib.ptr(S.bin_start), _lib.ptr(S.row_info), _lib.ptr(S.order),
-                                    _lib.ptr(E.sqnorm), db.id_offset, db.row_base, _lib.ptr(qi), _lib.ptr(E.packed), S.D,
-                                    _lib.ptr(q), S.D, _lib.ptr(p.bins[x, ps.q0:ps.q0 + ps.nq]), None, sp)
+        def restore():         # a valid sacc for the stages behind the scan
+            p.sacc_a.zero_()
+            p.sacc_t.zero_()
+            scan()
+
+        def bins():            # consume = 0: the same valid sacc for every repetition
+            lib.qpg_sliced_bins(tabs_b, 2, A.W, ps.nq, db.id_offset, db.row_base, 0, None, sp)
 
         def resolve():
-            for x, (E, q, qi, tab, rk, qf) in enumerate(((db.aud, p.qa, p.qinfo_a, p.ta, p.ra, p.qfa), (db.txt, p.qt, p.qinfo_t, p.tt, p.rt, p.qft))):
-                lib.qpg_sliced_resolve(_lib.ptr(p.parts[0, x]), 1, 2 * p.Q * 512, p.Qt, _lib.ptr(E.packed), E.D, _lib.ptr(E.sqnorm),
-                                       db.exact_offset, _lib.ptr(qi), _lib.ptr(q), E.D, _lib.ptr(tab), _lib.ptr(rk), _lib.ptr(qf), None, sp)
+            lib.qpg_sliced_resolve(tabs_r, 2, 1, 2 * p.Q * 512, p.Qt, db.exact_offset, None, sp)
 
         def lookup():
             lib.qpg_match_lookup(_lib.ptr(p.ta), _lib.ptr(p.tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank_t), _lib.ptr(db.freq_rank),
                                  _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft),
                                  p.Qt, _lib.ptr(p.entries), sp)
 
-        def walk():
+        def walk_table():
             lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
-                               p.n_tail, p.n_seg, _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
-        stages = dict(slice_queries=slice_q, zero_sacc=zero, scan=scan, scan_audio_only=scan_audio_only, bins=bins,
-                      resolve=resolve, lookup=lookup, walk=walk)
-        out["stage_us"] = {k: timed(f) for k, f in stages.items()}
+                               p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
+
+        def walk_direct():
+            lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
+                               p.n_tail, p.n_seg, None, _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
+        out["stage_us"] = {}
+        for name, f in (("slice_queries", slice_q), ("scan", scan), ("scan_audio_only", scan_audio_only)):
+            out["stage_us"][name] = timed(f)
+        restore()
+        stages = [("bins", bins), ("resolve", resolve), ("lookup", lookup), ("walk_direct", walk_direct)]
+        if p.trans is not None:
+            stages.append(("walk_table", walk_table))
+        for name, f in stages:
+            out["stage_us"][name] = timed(f)
+        p.sacc_a.zero_()
+        p.sacc_t.zero_()
         sliced_bytes = A.nbytes + T.nbytes
         alg_bytes = db.W * (4 * (db.aud.D + db.txt.D) + 4)
         out["scan_GBps_sliced_bytes"] = sliced_bytes / out["stage_us"]["scan"] / 1e3

@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Diagnostics of one sliced step: how many bins went through the float64 path, and why."""
+import os, sys, json
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from qpgesture_b200 import _lib
+from qpgesture_b200.GestureKNN import CodeKNN
+from qpgesture_b200.matchdb import MatchDatabase
+
+dev = torch.device("cuda")
+rng = np.random.default_rng(0)
+n = 512
+code = rng.integers(0, 512, size=(n, 30)).astype(np.int64)
+sig = rng.standard_normal((512, 135)).astype(np.float32)
+phase_amp = rng.standard_normal((n, 240, 16)).astype(np.float32)
+g = torch.Generator(device=dev); g.manual_seed(1)
+aud = torch.randn((n * 26, 6144), device=dev, generator=g)
+txt = torch.randn((n * 26, 384), device=dev, generator=g)
+db = MatchDatabase("A", code, sig, phase_amp, txt, aud_rows=aud, device=dev)
+knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, tail="device")
+p = knn.make_plan(1, 6, use_graph=False)
+p.qa.copy_(torch.randn(p.qa.shape, device=dev, generator=g))
+p.qt.copy_(torch.randn(p.qt.shape, device=dev, generator=g))
+p.seed_code.fill_(7)
+p.stats.zero_()
+knn.run_plan(p)
+torch.cuda.synchronize()
+# sacc was consumed by the bins stage: recompute it for the host-side recount
+lib = _lib.load()
+ps = p.passes[0]
+segs = (_lib.SlicedSeg * 2)()
+A, T = db.aud_s, db.txt_s
+segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.data_ptr(), ps.qs_a.data_ptr(), p.sacc_a.data_ptr(), A.n_kblocks
+segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
+lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, _lib.stream_ptr())
+torch.cuda.synchronize()
+bins = p.bins.cpu().numpy()            # [2, Q, 512, 4] int64
+out = {"stats": p.stats.cpu().tolist()}
+for x, name in enumerate(("audio", "text")):
+    b = bins[x]
+    lo = b[..., 0].view(np.float64); hi = b[..., 1].view(np.float64); ids = b[..., 2]
+    nf = b[..., 3]
+    ncand = (nf & 0xffffffff).astype(np.int64); flags = (nf >> 32).astype(np.int64)
+    nonempty = ids >= 0
+    out[name] = dict(nonempty=int(nonempty.sum()), exact=int(((flags & 1) != 0)[nonempty].sum()),
+                     n_hist=np.bincount(ncand[nonempty & ((flags & 1) != 0)], minlength=6)[:8].tolist(),
+                     width_max=float((hi - lo)[nonempty].max()), width_med=float(np.median((hi - lo)[nonempty])))
+    # recompute candidate counts on the host for query 0 from sacc
+    S = db.aud_s if x == 0 else db.txt_s
+    sacc = (p.sacc_a if x == 0 else p.sacc_t)[0, :S.W].cpu().numpy()
+    ri = S.row_info.cpu().numpy(); qi = (p.qinfo_a if x == 0 else p.qinfo_t)[0].cpu().numpy()
+    gq, h = qi[1], qi[2]
+    c = sacc.astype(np.float64) * (ri[:, 0] * 16777216.0) * gq
+    eps = gq * (ri[:, 0] * h + ri[:, 1]) * (1 + 1e-9) + 1e-12
+    d = 1.0 - c
+    bs = S.bin_start.cpu().numpy()
+    cnts = []
+    for cc in range(512):
+        a, e = bs[cc], bs[cc + 1]
+        if e > a:
+            U = (d[a:e] + eps[a:e]).min()
+            cnts.append(int(((d[a:e] - eps[a:e]) <= U).sum()))
+    out[name]["host_cand_hist_q0"] = np.bincount(cnts, minlength=4)[:6].tolist()
+    out[name]["eps_med"] = float(np.median(eps)); out[name]["sacc_absmax"] = int(np.abs(sacc).max())
+    out[name]["d_range"] = [float(d.min()), float(d.max())]
+print(json.dumps(out))
