@@ -64,17 +64,40 @@ __global__ void __launch_bounds__(256)
   }
   __syncthreads();
   // integer keys 20*(pos + rank) + freq order exactly like NumPy's float64 (pos + freq*0.05) + rank whenever
-  // they differ (the float64 rounding is ~1e-13, distinct keys are >= 0.05 apart)
-  int best[2] = {0x7fffffff, 0x7fffffff}, arg[2] = {0, 0}, ties[2] = {0, 0};
+  // they differ (the float64 rounding is ~1e-13, distinct keys are >= 0.05 apart).  On EQUAL keys NumPy compares
+  // the float64 values, which may differ in the last bits between different (pos, rank) splits: those are
+  // evaluated with NumPy's operation order right here; equal float64 values are a true tie (flagged).
+  auto f64_value = [&](int pos, int c, int x) {
+    const int fr = s_fr[c];
+    const int rk = ((s_key[x][c] & ~EMPTY) - fr) / 20;
+    return __dadd_rn(__dadd_rn((double)pos, __dmul_rn((double)fr, 0.05)), (double)rk);
+  };
+  int best[2] = {0x7fffffff, 0x7fffffff}, arg[2] = {0, 0}, bpos[2] = {0, 0}, tie[2] = {0, 0};
   int best_ne[2] = {0x7fffffff, 0x7fffffff};       // best key over non-empty bins
   int lb_e[2] = {0x3fffffff, 0x3fffffff};          // min over empty bins of 20*pos + freq
-  {
-    const int c0 = sl * CPS;
-    int pr[CPS];
+  auto offer = [&](int x, int key, int c, int pos, int t) {
+    if (key < best[x]) {
+      best[x] = key;
+      arg[x] = c;
+      bpos[x] = pos;
+      tie[x] = t;
+    } else if (key == best[x]) {
+      const double vb = f64_value(bpos[x], arg[x], x), vc = f64_value(pos, c, x);
+      if (vc < vb) {
+        arg[x] = c;
+        bpos[x] = pos;
+        tie[x] = t;
+      } else if (vc == vb) {
+        tie[x] = 1;                                // the lower code (offered first) stays
+      }
+    }
+  };
+  for (int c0 = sl * CPS; c0 < (sl + 1) * CPS; c0 += 8) {      // eight loads in flight per round
+    int pr[8];
 #pragma unroll
-    for (int i = 0; i < CPS; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
+    for (int i = 0; i < 8; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
 #pragma unroll
-    for (int i = 0; i < CPS; ++i) {
+    for (int i = 0; i < 8; ++i) {
       const int c = c0 + i;
       const int p20 = 20 * pr[i];
       const int fr = s_fr[c];
@@ -82,13 +105,7 @@ __global__ void __launch_bounds__(256)
       for (int x = 0; x < 2; ++x) {
         const int sk = s_key[x][c];
         const int key = p20 + (sk & ~EMPTY);
-        if (key < best[x]) {
-          best[x] = key;
-          arg[x] = c;
-          ties[x] = 1;
-        } else if (key == best[x]) {
-          ++ties[x];
-        }
+        offer(x, key, c, pr[i], 0);
         if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
         else best_ne[x] = min(best_ne[x], key);
       }
@@ -98,7 +115,7 @@ __global__ void __launch_bounds__(256)
   for (int x = 0; x < 2; ++x) {
     p_best[sl][x][l] = best[x];
     p_arg[sl][x][l] = arg[x];
-    p_ties[sl][x][l] = ties[x];
+    p_ties[sl][x][l] = (bpos[x] << 1) | tie[x];
     p_bne[sl][x][l] = best_ne[x];
     p_lbe[sl][x][l] = lb_e[x];
   }
@@ -108,14 +125,8 @@ __global__ void __launch_bounds__(256)
   for (int s2 = 1; s2 < NSL; ++s2) {
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-      const int b = p_best[s2][x][l];
-      if (b < best[x]) {
-        best[x] = b;
-        arg[x] = p_arg[s2][x][l];
-        ties[x] = p_ties[s2][x][l];
-      } else if (b == best[x]) {
-        ties[x] += p_ties[s2][x][l];
-      }
+      const int pt = p_ties[s2][x][l];
+      offer(x, p_best[s2][x][l], p_arg[s2][x][l], pt >> 1, pt & 1);
       best_ne[x] = min(best_ne[x], p_bne[s2][x][l]);
       lb_e[x] = min(lb_e[x], p_lbe[s2][x][l]);
     }
@@ -124,28 +135,7 @@ __global__ void __launch_bounds__(256)
   e.flags = ((qflags_a && qflags_a[q]) || (qflags_t && qflags_t[q])) ? 1 : 0;
 #pragma unroll
   for (int x = 0; x < 2; ++x) {
-    const int32_t* rank = x == 0 ? aud_rank : txt_rank;
-    if (ties[x] > 1) {
-      // equal integer keys: NumPy compares the float64 values, which may differ in the last bits between
-      // different (pos, rank) splits -> evaluate exactly those in float64 with NumPy's operation order
-      double bv = 1e300;
-      int bc = 0, nt = 0;
-      for (int c = 0; c < KB; ++c) {
-        const int pos = (int)pos_rank_t[(size_t)c * KB + last];
-        if (20 * pos + (s_key[x][c] & ~EMPTY) != best[x]) continue;
-        const int rk = rank[(size_t)q * KB + c];
-        const double v = __dadd_rn(__dadd_rn((double)pos, __dmul_rn((double)s_fr[c], 0.05)), (double)rk);
-        if (v < bv) {
-          bv = v;
-          bc = c;
-          nt = 1;
-        } else if (v == bv) {
-          ++nt;
-        }
-      }
-      arg[x] = bc;
-      if (nt > 1) e.flags |= 1;                    // a true tie at the arg-min: NumPy's order is platform defined
-    }
+    if (tie[x]) e.flags |= 1;                      // a true tie at the arg-min: NumPy's order is platform defined
     // empty bins all hold the sentinel 1e3, their mutual rank order is NumPy's business: the lowest rank any of
     // them can get is the number of non-empty bins.  If that could reach the best non-empty key, say so.
     const int ne = s_ne[x];
@@ -194,6 +184,32 @@ __device__ __forceinline__ int phase_pick(const float (&prev5)[5], const float* 
   float h[5];
 #pragma unroll
   for (int k = 0; k < 5; ++k) h[k] = head[k * PC + hl];
+  // float32 filter: both distances with ~1e-5 absolute error (vectors of 128 normalised components); decided
+  // when they are further apart than 1e-3.  Float64 division and square root cost ~20x more on this chip.
+  {
+    float sa = 0.f, sb = 0.f, ab = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float a = k < 5 ? prev5[k] : h[k - 5], b = k < 3 ? prev5[k + 2] : h[k - 3];
+      sa = fmaf(a, a, sa);
+      sb = fmaf(b, b, sb);
+      ab = fmaf(a, b, ab);
+    }
+#pragma unroll
+    for (int o = 8; o >= 1; o >>= 1) {
+      sa += __shfl_xor_sync(0xffffffffu, sa, o);
+      sb += __shfl_xor_sync(0xffffffffu, sb, o);
+      ab += __shfl_xor_sync(0xffffffffu, ab, o);
+    }
+    // 0.5*|a^ - b^|^2 = 0.5*(|a^|^2 + |b^|^2) - a^.b^  with |v^| = 1 unless v == 0 (then v^ = 0)
+    const float ia = sa > 0.f ? rsqrtf(sa) : 0.f, ib = sb > 0.f ? rsqrtf(sb) : 0.f;
+    const float d32 = 0.5f * ((sa > 0.f ? 1.f : 0.f) + (sb > 0.f ? 1.f : 0.f)) - ab * ia * ib;
+    const float da = __shfl_sync(0xffffffffu, d32, 0), dt = __shfl_sync(0xffffffffu, d32, 16);
+    // magnitudes: the float32 sums are only trusted when no component over/underflowed their squares
+    const bool sane = sa < 1e30f && sb < 1e30f && (sa == 0.f || sa > 1e-30f) && (sb == 0.f || sb > 1e-30f);
+    const bool all_sane = __all_sync(0xffffffffu, sane);
+    if (all_sane && fabsf(da - dt) > 1e-3f) return da < dt ? 0 : 1;
+  }
   double av[8], bv[8], sa = 0.0, sb = 0.0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -286,8 +302,8 @@ __global__ void __launch_bounds__(32)
 
 // ---- transitions: the pick for EVERY reachable state, in parallel (few clips: nothing left on the chain) ----
 // state entering step st = (last, which) of the winner of step st-1, i.e. window entries[q-1][last].w[which]
-// (step 0: the seed, state 0).  trans[q][state] = next state | tie flag << 10;  -1 = IndexError at this step,
-// -2 = unreachable.  One warp per (step, state).
+// (step 0: the seed, state 0).  trans[q][state] = next state | tie flag << 10;  -1 = IndexError at this step
+// (-3: and the choice that led there was tie dependent), -2 = unreachable.  One warp per (step, state).
 __global__ void __launch_bounds__(256)
     match_transition_kernel(const Entry* __restrict__ entries, const float* __restrict__ phase_amp,
                             const int32_t* __restrict__ seed_code, const float* __restrict__ seed_phase, int n_steps,
@@ -330,7 +346,7 @@ __global__ void __launch_bounds__(256)
   }
   const Entry e = load_entry(entries + q * KB + last);
   if (e.w[0] < 0 || e.w[1] < 0) {
-    if (lane == 0) trans[wid] = -1;
+    if (lane == 0) trans[wid] = (e.flags & 1) ? -3 : -1;       // IndexError (tie dependent: -3)
     return;
   }
   const long long w = hw == 0 ? e.w[0] : e.w[1];
@@ -367,7 +383,7 @@ __global__ void __launch_bounds__(256)
     for (; st < n_steps; ++st) {
       const int v = tab[st * 1024 + state];
       if (v < 0) {
-        status |= 1;
+        status |= v == -3 ? 3 : 1;
         break;
       }
       status |= (v >> 10) & 1 ? 2 : 0;

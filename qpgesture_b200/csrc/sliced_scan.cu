@@ -551,8 +551,10 @@ __global__ void __launch_bounds__(256)
   rec.flags = 0;
   if (b1 > b0) {
     double U = 1e300;
+    Interval iv0{0.0, 0.0};                       // first chunk of 32 rows (most bins have no more): kept for pass 2
     for (int pos = b0 + lane; pos < b1; pos += 32) {
       const Interval iv = filter_interval(sv[pos], T.row_info[pos], qi);
+      if (pos < b0 + 32) iv0 = iv;
       U = fmin(U, iv.hi);
     }
 #pragma unroll
@@ -565,7 +567,7 @@ __global__ void __launch_bounds__(256)
       bool cand = false;
       Interval iv{0.0, 0.0};
       if (pos < b1) {
-        iv = filter_interval(sv[pos], T.row_info[pos], qi);
+        iv = base == b0 ? iv0 : filter_interval(sv[pos], T.row_info[pos], qi);
         cand = iv.lo <= U;
         if (consume) sv[pos] = 0;
       }
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(KB)
     sliced_resolve_kernel(const TablePair tp, int P, long long part_stride, int64_t first_id,
                           unsigned long long* __restrict__ stats) {
-  __shared__ double s_lo[KB], s_hi[KB];
+  __shared__ double2 s_iv[KB];                  // (lo, hi); empty bins (1e3, 1e3)
   __shared__ unsigned long long s_d[KB];
   __shared__ long long s_id[KB];
   __shared__ int s_list[KB];
@@ -667,19 +669,19 @@ __global__ void __launch_bounds__(KB)
     }
   }
   if (ncand > 0) hi = U;
-  s_lo[c] = lo;
-  s_hi[c] = hi;
+  s_iv[c] = make_double2(lo, hi);
   __syncthreads();
   // a bin needs a float64 decision when several shards could hold its winner, or when its interval overlaps
   // another bin's (the rank transform would be undecided); exact points need nothing
   bool need = ncand > 1;
   if (ncand == 1 && !(exact && lo == hi)) {
+    int ov = 0;
+#pragma unroll 8
     for (int j = 0; j < KB; ++j) {
-      if (j != c && s_lo[j] <= hi && lo <= s_hi[j] && s_hi[j] < kEmptyDist) {
-        need = true;
-        break;
-      }
+      const double2 o = s_iv[j];
+      ov += (o.x <= hi) & (lo <= o.y) & (o.y < kEmptyDist);
     }
+    need = ov > 1;                              // the bin always overlaps itself
   }
   if (need) s_list[atomicAdd(&s_n, 1)] = c;
   __syncthreads();
@@ -691,7 +693,7 @@ __global__ void __launch_bounds__(KB)
   const float* qrow = T.q + (size_t)qi_ * T.ldq;
   for (int it = warp; it < n_list; it += KB / 32) {
     const int cc = s_list[it];
-    const double Uc = s_hi[cc];
+    const double Uc = s_iv[cc].y;
     double bd = 1e300;
     long long bid = -1;
     for (int p = 0; p < P; ++p) {
