@@ -51,16 +51,22 @@ __global__ void __launch_bounds__(256)
   __shared__ int p_best[NSL][2][32], p_arg[NSL][2][32], p_ties[NSL][2][32], p_bne[NSL][2][32], p_lbe[NSL][2][32];
   const int q = blockIdx.x, tid = threadIdx.x, l = tid & 31, sl = tid >> 5;
   const int last = blockIdx.y * 32 + l;
-  if (tid < 2) s_ne[tid] = 0;
-  __syncthreads();
+  int ne_a = 0, ne_t = 0;
   for (int c = tid; c < KB; c += 256) {
     const int fr = freq_rank[c];
     const long long ida = (long long)aud_table[(size_t)q * KB + c].id, idt = (long long)txt_table[(size_t)q * KB + c].id;
     s_fr[c] = fr;
     s_key[0][c] = (20 * aud_rank[(size_t)q * KB + c] + fr) | (ida < 0 ? EMPTY : 0);
     s_key[1][c] = (20 * txt_rank[(size_t)q * KB + c] + fr) | (idt < 0 ? EMPTY : 0);
-    if (ida >= 0) atomicAdd(&s_ne[0], 1);
-    if (idt >= 0) atomicAdd(&s_ne[1], 1);
+    ne_a += ida >= 0;
+    ne_t += idt >= 0;
+  }
+  // every thread staged exactly two codes: count the non-empty bins with two block-wide popcounts
+  const int na1 = __syncthreads_count(ne_a >= 1), na2 = __syncthreads_count(ne_a >= 2);
+  const int nt1 = __syncthreads_count(ne_t >= 1), nt2 = __syncthreads_count(ne_t >= 2);
+  if (tid == 0) {
+    s_ne[0] = na1 + na2;
+    s_ne[1] = nt1 + nt2;
   }
   __syncthreads();
   // integer keys 20*(pos + rank) + freq order exactly like NumPy's float64 (pos + freq*0.05) + rank whenever
@@ -304,7 +310,7 @@ __global__ void __launch_bounds__(32)
 // state entering step st = (last, which) of the winner of step st-1, i.e. window entries[q-1][last].w[which]
 // (step 0: the seed, state 0).  trans[q][state] = next state | tie flag << 10;  -1 = IndexError at this step
 // (-3: and the choice that led there was tie dependent), -2 = unreachable.  One warp per (step, state).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
     match_transition_kernel(const Entry* __restrict__ entries, const float* __restrict__ phase_amp,
                             const int32_t* __restrict__ seed_code, const float* __restrict__ seed_phase, int n_steps,
                             long long n_warps, int16_t* __restrict__ trans) {

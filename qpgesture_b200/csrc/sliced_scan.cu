@@ -69,10 +69,15 @@ struct SliceJobs {
   SliceJob j[2];
 };
 
+// 2^e as a double, |e| < 1000 (exact; multiplying by it is exact unless the result is subnormal)
+__device__ __forceinline__ double pow2(int e) { return __hiloint2double((1023 + e) << 20, 0); }
+
+constexpr int SLICE_THREADS = 256;
 template <bool kQuery>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(SLICE_THREADS)
     slice_kernel(const SliceJobs jobs, const int32_t* __restrict__ order, int n_pad,
                  const double* __restrict__ sqnorm_in, RowInfo* __restrict__ row_info) {
+  constexpr int NW = SLICE_THREADS / 32;
   const SliceJob job = blockIdx.y == 0 ? jobs.j[0] : jobs.j[1];
   const float* __restrict__ rows = job.rows;
   const int8_t* __restrict__ col_exp = job.col_exp;
@@ -80,8 +85,8 @@ __global__ void __launch_bounds__(128)
   qpg_qinfo_t* __restrict__ q_info = job.q_info;
   const int64_t ld = job.ld;
   const int D = job.D, nkb = job.nkb;
-  __shared__ double s_red[4];
-  __shared__ unsigned long long s_l1[4], s_el[4];
+  __shared__ double s_red[NW];
+  __shared__ unsigned long long s_l1[NW], s_el[NW];
   __shared__ int s_ex;
   const int64_t pos = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -91,10 +96,10 @@ __global__ void __launch_bounds__(128)
 
   // pass 1: maximum magnitude (after the column scaling) and, for queries, the squared norm
   double mx = 0.0, sq = 0.0;
-  for (int k = tid; k < D; k += 128) {
+  for (int k = tid; k < D; k += SLICE_THREADS) {
     double v = (double)x[k];
     sq = fma(v, v, sq);
-    if (col_exp) v = scalbn(v, kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
+    if (col_exp) v *= pow2(kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
     mx = fmax(mx, fabs(v));
   }
 #pragma unroll
@@ -102,43 +107,47 @@ __global__ void __launch_bounds__(128)
   if (lane == 0) s_red[warp] = mx;
   __syncthreads();
   if (tid == 0) {
-    const double m = fmax(fmax(s_red[0], s_red[1]), fmax(s_red[2], s_red[3]));
+    double m = s_red[0];
+#pragma unroll
+    for (int w = 1; w < NW; ++w) m = fmax(m, s_red[w]);
     s_ex = m > 0.0 ? ilogb(m) + 1 : 0;         // |x'| < 2^ex
   }
   __syncthreads();
   const int ex = s_ex;
-  if (kQuery) {   // squared norm in a fixed order (lane-strided partials, shuffle tree, 4 warps in order)
+  if (kQuery) {   // squared norm in a fixed order (thread-strided partials, shuffle tree, warps in order)
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
     if (lane == 0) s_red[warp] = sq;           // s_red reuse is safe: everyone passed the barrier above
   }
 
-  // pass 2: digits.  Thread t owns columns 4t..4t+3 of every 512-column stripe -> one 32-bit store per slice
-  unsigned long long l1 = 0, el = 0;
+  // pass 2: digits.  Thread t owns columns 4t..4t+3 of every 1024-column stripe -> one 32-bit store per slice
+  unsigned long long l1 = 0;
+  unsigned int el = 0;
   const int64_t tile_row = kQuery ? pos : (pos % TM);
   const int64_t rt = kQuery ? 0 : pos / TM;
-  for (int k0 = 4 * tid; k0 < Dp; k0 += 512) {
+  const double scale = pow2(30 - ex);           // ex in [-148, 129] for float32 data
+  for (int k0 = 4 * tid; k0 < Dp; k0 += 4 * SLICE_THREADS) {
     uint32_t w[NS] = {0u, 0u, 0u, 0u};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int k = k0 + i;
-      long long X = 0;
+      int X = 0;
       if (k < D) {
         double v = (double)x[k];
-        if (col_exp) v = scalbn(v, kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
-        X = llrint(scalbn(v, 30 - ex));
+        if (col_exp) v *= pow2(kQuery ? (int)col_exp[k] : -(int)col_exp[k]);
+        X = __double2int_rn(v * scale);          // |X| <= 2^30
       }
       l1 += (unsigned long long)(X < 0 ? -X : X);
-      long long r = X;
+      int r = X;
       int dig[NS];
 #pragma unroll
       for (int s = NS - 1; s >= 1; --s) {
-        const long long d = ((r + 128) & 255) - 128;
-        dig[s] = (int)d;
+        const int d = ((r + 128) & 255) - 128;
+        dig[s] = d;
         r = (r - d) >> 8;
-        el += (unsigned long long)(d < 0 ? -d : d);
+        el += (unsigned int)(d < 0 ? -d : d);
       }
-      dig[0] = (int)r;                           // |r| <= 64 because |X| <= 2^30
+      dig[0] = r;                                // |r| <= 64 because |X| <= 2^30
 #pragma unroll
       for (int s = 0; s < NS; ++s) w[s] |= ((uint32_t)dig[s] & 0xffu) << (8 * i);
     }
@@ -150,24 +159,31 @@ __global__ void __launch_bounds__(128)
       *reinterpret_cast<uint32_t*>(out + base + swz_offset((uint32_t)tile_row, (uint32_t)kbyte)) = w[s];
     }
   }
+  unsigned long long el64 = el;
 #pragma unroll
   for (int o = 16; o >= 1; o >>= 1) {
     l1 += __shfl_xor_sync(0xffffffffu, l1, o);
-    el += __shfl_xor_sync(0xffffffffu, el, o);
+    el64 += __shfl_xor_sync(0xffffffffu, el64, o);
   }
   if (lane == 0) {
     s_l1[warp] = l1;
-    s_el[warp] = el;
+    s_el[warp] = el64;
   }
   __syncthreads();
   if (tid == 0) {
-    const double L1 = (double)(s_l1[0] + s_l1[1] + s_l1[2] + s_l1[3]);
-    const double EL = (double)(s_el[0] + s_el[1] + s_el[2] + s_el[3]);
+    unsigned long long t1 = 0, t2 = 0;
+    double sqq = 0.0;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      t1 += s_l1[w];
+      t2 += s_el[w];
+      if (kQuery) sqq += s_red[w];
+    }
+    const double L1 = (double)t1, EL = (double)t2;
     if (kQuery) {
-      const double sqq = ((s_red[0] + s_red[1]) + s_red[2]) + s_red[3];
       qpg_qinfo_t qi;
       qi.sq = sqq;
-      qi.g = sqq > kTinySq ? scalbn(1.0, ex) / sqrt(sqq) : 0.0;
+      qi.g = sqq > kTinySq ? pow2(ex) / sqrt(sqq) : 0.0;
       qi.h = 0.5 * L1 + DROP_C * EL + 0.25 * (double)D;
       qi.ex = ex;
       qi.pad = 0;
@@ -175,7 +191,7 @@ __global__ void __launch_bounds__(128)
     } else {
       const double sqx = sqnorm_in[src];
       RowInfo ri;
-      ri.r1 = sqx > kTinySq ? scalbn(1.0, ex - 60) / sqrt(sqx) : 0.0;
+      ri.r1 = sqx > kTinySq ? pow2(ex - 60) / sqrt(sqx) : 0.0;
       ri.r2 = 0.5 * L1 * ri.r1;
       row_info[pos] = ri;
     }
@@ -440,7 +456,7 @@ __global__ void sliced_scan_ref_kernel(const int8_t* __restrict__ A, const int8_
 // ------------------------------------------------------------------ exact float64 re-evaluation
 // distance of query `q` (float32 [D], squared norm sqq) to row w of a float32 table in the 4 KiB tile
 // layout of qpg_pack_rows_f32; warp-cooperative, fixed summation order, result on every lane.
-__device__ __forceinline__ double exact_distance(const float* __restrict__ packed, int NC, int64_t w,
+__device__ __noinline__ double exact_distance(const float* __restrict__ packed, int NC, int64_t w,
                                                  const float* __restrict__ q, int D, double sqq, double sqx, int lane) {
   const float* base = packed + (((size_t)(w >> 3) * NC) * 8 + (w & 7)) * 128;
   double acc = 0.0;
@@ -531,9 +547,9 @@ struct TablePair {
 // reaches below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly those
 // rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  With `consume` the entries of sacc are
 // zeroed once read, so the next pass needs no memset.
-__global__ void __launch_bounds__(256)
-    sliced_bins_kernel(const TablePair tp, long long Wpad, int nq, int64_t id_offset, int64_t row_base, int consume,
-                       unsigned long long* __restrict__ stats) {
+__global__ void __launch_bounds__(256, 4)
+    sliced_bins_kernel(const TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset, int64_t row_base,
+                       int consume, unsigned long long* __restrict__ stats) {
   const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
@@ -620,6 +636,8 @@ __global__ void __launch_bounds__(256)
     rec.flags = 1;                           // empty bins are exact (sentinel)
   }
   if (lane == 0) T.bins[(size_t)qi_ * KB + c] = rec;
+  if (consume && c == KB - 1)                    // rows with a label outside [0, 512) belong to no bin
+    for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
 }
 
 // ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
@@ -771,7 +789,7 @@ extern "C" int qpg_slice_rows_i8(const float* rows, int64_t W, int D, const int3
   jobs.j[0].D = D;
   jobs.j[0].nkb = (D + KBW - 1) / KBW;
   jobs.j[1] = jobs.j[0];
-  slice_kernel<false><<<dim3((unsigned)W, 1), 128, 0, st>>>(jobs, order, 0, row_sqnorm,
+  slice_kernel<false><<<dim3((unsigned)W, 1), SLICE_THREADS, 0, st>>>(jobs, order, 0, row_sqnorm,
                                                            reinterpret_cast<RowInfo*>(row_info));
   QPG_LAUNCH_CHECK();
   return QPG_OK;
@@ -799,7 +817,7 @@ extern "C" int qpg_slice_queries_i8(const qpg_slice_job_t* jobs_in, int n_jobs, 
     jobs.j[i].nkb = (j.D + KBW - 1) / KBW;
   }
   if (n_jobs == 1) jobs.j[1] = jobs.j[0];
-  slice_kernel<true><<<dim3((unsigned)Q, (unsigned)n_jobs), 128, 0, st>>>(jobs, nullptr, n_pad, nullptr, nullptr);
+  slice_kernel<true><<<dim3((unsigned)Q, (unsigned)n_jobs), SLICE_THREADS, 0, st>>>(jobs, nullptr, n_pad, nullptr, nullptr);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
@@ -896,7 +914,7 @@ extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64
   const long long Wpad = (W + TM - 1) / TM * TM;
   const long long warps = (long long)nq * KB;
   const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);
-  sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, Wpad, nq, id_offset, row_base, consume,
+  sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
                                                              reinterpret_cast<unsigned long long*>(stats));
   QPG_LAUNCH_CHECK();
   return QPG_OK;
