@@ -36,7 +36,7 @@ struct __align__(16) Entry {
 static_assert(sizeof(Entry) == 32, "entry is 32 bytes");
 
 // grid (Q, 16), 256 threads: lane = one of 32 values of `last`, warp = one 64-code slice of the scan
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 6)
     match_lookup_kernel(const Pair* __restrict__ aud_table, const Pair* __restrict__ txt_table,
                         const int32_t* __restrict__ aud_rank, const int32_t* __restrict__ txt_rank,
                         const int16_t* __restrict__ pos_rank_t, const int32_t* __restrict__ freq_rank,
@@ -98,22 +98,33 @@ __global__ void __launch_bounds__(256)
       }
     }
   };
+  const bool any_empty = s_ne[0] < KB || s_ne[1] < KB;          // block uniform; false for any sizeable database
   for (int c0 = sl * CPS; c0 < (sl + 1) * CPS; c0 += 8) {      // eight loads in flight per round
     int pr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
+    if (!any_empty) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int c = c0 + i;
-      const int p20 = 20 * pr[i];
-      const int fr = s_fr[c];
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const int p20 = 20 * pr[i];
+        offer(0, p20 + s_key[0][c], c, pr[i], 0);
+        offer(1, p20 + s_key[1][c], c, pr[i], 0);
+      }
+    } else {
 #pragma unroll
-      for (int x = 0; x < 2; ++x) {
-        const int sk = s_key[x][c];
-        const int key = p20 + (sk & ~EMPTY);
-        offer(x, key, c, pr[i], 0);
-        if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
-        else best_ne[x] = min(best_ne[x], key);
+      for (int i = 0; i < 8; ++i) {
+        const int c = c0 + i;
+        const int p20 = 20 * pr[i];
+        const int fr = s_fr[c];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int sk = s_key[x][c];
+          const int key = p20 + (sk & ~EMPTY);
+          offer(x, key, c, pr[i], 0);
+          if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
+          else best_ne[x] = min(best_ne[x], key);
+        }
       }
     }
   }

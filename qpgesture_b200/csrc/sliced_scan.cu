@@ -15,6 +15,8 @@
 // and the queries likewise (Y, digits e_t).  The kernel accumulates the ten digit products with
 // s+t <= 3, P_j = sum_{s+t=j} sum_k d_s[k] e_t[k], EXACTLY (integers), so
 //   dot(x,q) = 2^(ex+eq-36) * v + R,   v = P0*2^24 + P1*2^16 + P2*2^8 + P3  (int64),
+// (issued as four instructions per 32-column k-step: slice s of the rows against the stacked query slices
+//  0..3-s, so that products of equal weight s+t accumulate in the same TMEM columns)
 //   |R| <= 2^(ex+eq-60) * (L1(X)/2 + L1(Y)/2 + K/4 + 128*65793*sum_k(|e1|+|e2|+|e3|))
 // (quantisation |dX|,|dY| <= 1/2 plus the six dropped products, |d_s| <= 128).  That is a cosine error
 // of ~1e-7 on Gaussian data with a rigorous, per-(row,query) bound: every distance is an interval
@@ -324,11 +326,16 @@ __global__ void __launch_bounds__(256, 1) sliced_scan_kernel(const ScanParams p)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer: 4 k-steps x 10 digit products per unit =====
+    // ===== MMA issuer: 4 k-steps x 4 MMAs per unit =====
+    // The ten digit products with s + t <= 3 are issued as FOUR instructions per k-step: A slice s against the
+    // query slices 0..3-s stacked along N (they are contiguous 8-row-aligned tiles in shared memory, so
+    // [B_0; ..; B_{3-s}] is itself a valid K-major SWIZZLE_128B operand with N = n_pad*(4-s) rows), written at
+    // column offset s*n_pad: product (s, t) lands in column block s + t, i.e. products of equal weight share an
+    // accumulator, and every A slice is fetched from shared memory once per k-step instead of up to four times
+    // (operand fetch, not the tensor pipe, was the limiter: 96 cycles per N = 48 instruction measured).
     if (lane == 0) {
       // D = S32 (2 << 4), A = B = signed int8 (1 << 7, 1 << 10), both K-major, N >> 3 at bit 17, M >> 4 at bit 24
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_pad >> 3) << 17) |
-                             ((uint32_t)(TM >> 4) << 24);
+      const uint32_t idesc0 = (2u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(TM >> 4) << 24);
       int it = 0, run = 0;
       bool first = true;
       for (long long u = u0; u < u1; ++u, ++it) {
@@ -344,17 +351,15 @@ __global__ void __launch_bounds__(256, 1) sliced_scan_kernel(const ScanParams p)
         const uint32_t a_addr = smem_u32(smem + (size_t)s * stage_bytes);
         const uint32_t b_addr = a_addr + NS * SLICE_BYTES;
         const uint32_t acc0 = tmem_base + (uint32_t)(as * NS * p.n_pad);
+        const uint64_t b_desc0 = umma_desc_sw128(b_addr);
 #pragma unroll
         for (int k4 = 0; k4 < KBW / 32; ++k4) {
 #pragma unroll
-          for (int j = 0; j < NS; ++j) {
-#pragma unroll
-            for (int sa = 0; sa <= j; ++sa) {
-              const int tb = j - sa;
-              const uint64_t a_desc = umma_desc_sw128(a_addr + sa * SLICE_BYTES) + 2u * k4;
-              const uint64_t b_desc = umma_desc_sw128(b_addr + tb * b_slice_bytes) + 2u * k4;
-              tc_mma_i8(acc0 + (uint32_t)(j * p.n_pad), a_desc, b_desc, idesc, (first && k4 == 0 && sa == 0) ? 0u : 1u);
-            }
+          for (int sa = 0; sa < NS; ++sa) {
+            const uint32_t n_rows = (uint32_t)(p.n_pad * (NS - sa));
+            const uint64_t a_desc = umma_desc_sw128(a_addr + sa * SLICE_BYTES) + 2u * k4;
+            tc_mma_i8(acc0 + (uint32_t)(sa * p.n_pad), a_desc, b_desc0 + 2u * k4, idesc0 | ((n_rows >> 3) << 17),
+                      (first && k4 == 0 && sa == 0) ? 0u : 1u);
           }
         }
         tc_commit(&empty[s]);
@@ -508,11 +513,21 @@ __device__ __noinline__ double exact_distance(const float* __restrict__ packed, 
 struct Interval {
   double lo, hi;
 };
+struct QConst {          // what filter_interval needs of a query: 2^eq/|q| and the bound terms premultiplied
+  double g, gh, g1;      // g, g*h*(1+1e-9), g*(1+1e-9)
+};
+__device__ __forceinline__ QConst make_qconst(const qpg_qinfo_t& qi) {
+  QConst c;
+  c.g = qi.g;
+  c.gh = qi.g * qi.h * (1.0 + 1e-9);
+  c.g1 = qi.g * (1.0 + 1e-9);
+  return c;
+}
 // distance interval of (query, sorted row) from the exact integer v
-__device__ __forceinline__ Interval filter_interval(long long v, const RowInfo ri, const qpg_qinfo_t& qi) {
-  const double a = qi.g > 0.0 ? 1.0 : 0.0, b = ri.r1 > 0.0 ? 1.0 : 0.0;
-  const double c = (double)v * (ri.r1 * 16777216.0) * qi.g;                 // 2^(ex+eq-36) v / (|x||q|)
-  const double eps = (qi.g * fma(ri.r1, qi.h, ri.r2)) * (1.0 + 1e-9) + EPS_SLACK;
+__device__ __forceinline__ Interval filter_interval(long long v, const RowInfo ri, const QConst& qc) {
+  const double a = qc.g > 0.0 ? 1.0 : 0.0, b = ri.r1 > 0.0 ? 1.0 : 0.0;
+  const double c = (double)v * (ri.r1 * 16777216.0) * qc.g;                 // 2^(ex+eq-36) v / (|x||q|)
+  const double eps = fma(ri.r1, qc.gh, ri.r2 * qc.g1) + EPS_SLACK;          // >= g*(r1*h + r2), see header
   const double d = 0.5 * (a + b) - c;
   Interval iv;
   iv.lo = d - eps;
@@ -543,101 +558,131 @@ struct TablePair {
   TableParams t[2];
 };
 
-// One warp per (table, query, start code): U = min hi over the bin's rows; candidates = rows whose interval
-// reaches below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly those
-// rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  With `consume` the entries of sacc are
-// zeroed once read, so the next pass needs no memset.
-__global__ void __launch_bounds__(256, 4)
+// One warp per (table, start code, group of BG queries): U = min hi over the bin's rows; candidates = rows whose
+// interval reaches below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly
+// those rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  BG queries share one trip over the
+// bin's rows (row_info is loaded once, the BG sacc loads are independent: the kernel is latency bound).  With
+// `consume` the entries of sacc are zeroed once read, so the next pass needs no memset.
+constexpr int BG = 4;
+__global__ void __launch_bounds__(256, 2)
     sliced_bins_kernel(const TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset, int64_t row_base,
                        int consume, unsigned long long* __restrict__ stats) {
   const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
   const int lane = threadIdx.x & 31;
   const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  if (wid >= (long long)nq * KB) return;
-  const int qi_ = (int)(wid / KB), c = (int)(wid % KB);
-  const qpg_qinfo_t qi = T.q_info[qi_];
+  const int n_groups = (nq + BG - 1) / BG;
+  if (wid >= (long long)n_groups * KB) return;
+  const int q0 = (int)(wid / KB) * BG, c = (int)(wid % KB);
   const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
-  long long* sv = T.sacc + (size_t)qi_ * Wpad;
-  const float* qrow = T.q + (size_t)qi_ * T.ldq;
-  qpg_bin_t rec;
-  rec.lo = kEmptyDist;
-  rec.hi = kEmptyDist;
-  rec.id = -1;
-  rec.n = 0;
-  rec.flags = 0;
-  if (b1 > b0) {
-    double U = 1e300;
-    Interval iv0{0.0, 0.0};                       // first chunk of 32 rows (most bins have no more): kept for pass 2
-    for (int pos = b0 + lane; pos < b1; pos += 32) {
-      const Interval iv = filter_interval(sv[pos], T.row_info[pos], qi);
-      if (pos < b0 + 32) iv0 = iv;
-      U = fmin(U, iv.hi);
-    }
+  QConst qi[BG];
 #pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) U = fmin(U, __shfl_xor_sync(0xffffffffu, U, o));
-    int n = 0;
-    double best_lo = 1e300, best_d = 1e300;
-    long long best_id = -1, single_pos = -1;
-    for (int base = b0; base < b1; base += 32) {
-      const int pos = base + lane;
-      bool cand = false;
-      Interval iv{0.0, 0.0};
-      if (pos < b1) {
-        iv = base == b0 ? iv0 : filter_interval(sv[pos], T.row_info[pos], qi);
-        cand = iv.lo <= U;
-        if (consume) sv[pos] = 0;
-      }
-      const unsigned m = __ballot_sync(0xffffffffu, cand);
-      const int cnt = __popc(m);
-      if (cnt == 0) continue;
-      if (n == 0 && cnt == 1) {            // remember the first lone candidate; verified later only if another shows up
-        const int src_lane = __ffs(m) - 1;
-        single_pos = base + src_lane;
-        best_lo = __shfl_sync(0xffffffffu, iv.lo, src_lane);
-        n = 1;
-        continue;
-      }
-      // more than one candidate so far: evaluate exactly (including the remembered one)
-      if (n == 1 && single_pos >= 0) {
-        const long long w = T.order[single_pos];
-        const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, qi.sq, T.sqnorm[w + row_base], lane);
-        best_d = d;
-        best_id = id_offset + w;
-        single_pos = -1;
-      }
-      unsigned mm = m;
-      while (mm) {
-        const int src_lane = __ffs(mm) - 1;
-        mm &= mm - 1;
-        const long long w = T.order[base + src_lane];
-        const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, qi.sq, T.sqnorm[w + row_base], lane);
-        const long long id = id_offset + w;
-        if (d < best_d || (d == best_d && id < best_id)) {
-          best_d = d;
-          best_id = id;
-        }
-      }
-      n += cnt;
-    }
-    if (n == 1 && single_pos >= 0) {
-      rec.lo = best_lo;
-      rec.hi = U;
-      rec.id = id_offset + T.order[single_pos];
-      rec.n = 1;
-    } else {
-      rec.lo = best_d;
-      rec.hi = best_d;
-      rec.id = best_id;
-      rec.n = n;                             // how many rows were re-evaluated (diagnostics)
-      rec.flags = 1;                         // exact
-      if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
-    }
-  } else {
-    rec.flags = 1;                           // empty bins are exact (sentinel)
+  for (int g = 0; g < BG; ++g) qi[g] = make_qconst(T.q_info[min(q0 + g, nq - 1)]);
+  double U[BG], lo0[BG], hi0[BG];
+#pragma unroll
+  for (int g = 0; g < BG; ++g) {
+    U[g] = 1e300;
+    lo0[g] = hi0[g] = 0.0;
   }
-  if (lane == 0) T.bins[(size_t)qi_ * KB + c] = rec;
-  if (consume && c == KB - 1)                    // rows with a label outside [0, 512) belong to no bin
-    for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
+  // pass 1: U per query; the intervals of the first 32 rows (most bins have no more) stay in registers
+  for (int pos = b0 + lane; pos < b1; pos += 32) {
+    const RowInfo ri = T.row_info[pos];
+    long long v[BG];
+#pragma unroll
+    for (int g = 0; g < BG; ++g) v[g] = T.sacc[(size_t)min(q0 + g, nq - 1) * Wpad + pos];
+#pragma unroll
+    for (int g = 0; g < BG; ++g) {
+      const Interval iv = filter_interval(v[g], ri, qi[g]);
+      if (pos < b0 + 32) {
+        lo0[g] = iv.lo;
+        hi0[g] = iv.hi;
+      }
+      U[g] = fmin(U[g], iv.hi);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < BG; ++g)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) U[g] = fmin(U[g], __shfl_xor_sync(0xffffffffu, U[g], o));
+
+#pragma unroll 1
+  for (int g = 0; g < BG; ++g) {
+    const int qi_ = q0 + g;
+    if (qi_ >= nq) break;
+    long long* sv = T.sacc + (size_t)qi_ * Wpad;
+    const float* qrow = T.q + (size_t)qi_ * T.ldq;
+    const QConst qg = g == 0 ? qi[0] : g == 1 ? qi[1] : g == 2 ? qi[2] : qi[3];
+    const double sqq = T.q_info[qi_].sq;
+    const double Ug = g == 0 ? U[0] : g == 1 ? U[1] : g == 2 ? U[2] : U[3];
+    const double l0 = g == 0 ? lo0[0] : g == 1 ? lo0[1] : g == 2 ? lo0[2] : lo0[3];
+    qpg_bin_t rec;
+    rec.lo = kEmptyDist;
+    rec.hi = kEmptyDist;
+    rec.id = -1;
+    rec.n = 0;
+    rec.flags = 1;                               // empty bins are exact (sentinel)
+    if (b1 > b0) {
+      int n = 0;
+      double best_lo = 1e300, best_d = 1e300;
+      long long best_id = -1, single_pos = -1;
+      for (int base = b0; base < b1; base += 32) {
+        const int pos = base + lane;
+        bool cand = false;
+        double lo = 0.0;
+        if (pos < b1) {
+          lo = base == b0 ? l0 : filter_interval(sv[pos], T.row_info[pos], qg).lo;
+          cand = lo <= Ug;
+          if (consume) sv[pos] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        const int cnt = __popc(m);
+        if (cnt == 0) continue;
+        if (n == 0 && cnt == 1) {          // remember the first lone candidate; verified only if another shows up
+          const int src_lane = __ffs(m) - 1;
+          single_pos = base + src_lane;
+          best_lo = __shfl_sync(0xffffffffu, lo, src_lane);
+          n = 1;
+          continue;
+        }
+        // more than one candidate so far: evaluate exactly (including the remembered one)
+        if (n == 1 && single_pos >= 0) {
+          const long long w = T.order[single_pos];
+          best_d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+          best_id = id_offset + w;
+          single_pos = -1;
+        }
+        unsigned mm = m;
+        while (mm) {
+          const int src_lane = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const long long w = T.order[base + src_lane];
+          const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+          const long long id = id_offset + w;
+          if (d < best_d || (d == best_d && id < best_id)) {
+            best_d = d;
+            best_id = id;
+          }
+        }
+        n += cnt;
+      }
+      if (n == 1 && single_pos >= 0) {
+        rec.lo = best_lo;
+        rec.hi = Ug;
+        rec.id = id_offset + T.order[single_pos];
+        rec.n = 1;
+        rec.flags = 0;
+      } else {
+        rec.lo = best_d;
+        rec.hi = best_d;
+        rec.id = best_id;
+        rec.n = n;                           // how many rows were re-evaluated (diagnostics)
+        rec.flags = 1;                       // exact
+        if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
+      }
+    }
+    if (lane == 0) T.bins[(size_t)qi_ * KB + c] = rec;
+    if (consume && c == KB - 1)                  // rows with a label outside [0, 512) belong to no bin
+      for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
+  }
 }
 
 // ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
@@ -647,17 +692,43 @@ __global__ void __launch_bounds__(256, 4)
 // whole table), so any rank can re-evaluate any candidate.  Output: table [nq][512] (distance exact where it had
 // to be decided, else the centre of the filter interval), ranks [nq][512] (stable, as qpg_rank512),
 // qflags [nq] bit 0 = exact tie between two non-empty bins.
+// ascending bitonic sort of 512 (key, val) pairs in shared memory by 512 threads; vals are distinct, so the order
+// is total: equal keys keep the lower val first
+__device__ __forceinline__ void bitonic_sort_512(unsigned long long* key, int* val, int tid) {
+  for (int k = 2; k <= KB; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      const int other = tid ^ j;
+      unsigned long long kk = key[tid], ok = key[other];
+      int vv = val[tid], ov = val[other];
+      __syncthreads();
+      const bool want_min = ((tid & k) == 0) == (tid < other);
+      const bool other_less = ok < kk || (ok == kk && ov < vv);
+      if (other_less == want_min) {
+        kk = ok;
+        vv = ov;
+      }
+      key[tid] = kk;
+      val[tid] = vv;
+      __syncthreads();
+    }
+  }
+}
+
 __global__ void __launch_bounds__(KB)
     sliced_resolve_kernel(const TablePair tp, int P, long long part_stride, int64_t first_id,
                           unsigned long long* __restrict__ stats) {
-  __shared__ double2 s_iv[KB];                  // (lo, hi); empty bins (1e3, 1e3)
+  __shared__ unsigned long long s_key[KB];       // sort keys: lo bits (first sort), final distance bits (second)
+  __shared__ int s_val[KB];
+  __shared__ unsigned long long s_hi[KB];        // hi bits by code, then running maximum by sorted position
+  __shared__ unsigned long long s_pm[KB];
   __shared__ unsigned long long s_d[KB];
   __shared__ long long s_id[KB];
-  __shared__ int s_list[KB];
+  __shared__ int s_ov[KB], s_list[KB];
   __shared__ int s_n, s_tie;
   const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
   const qpg_bin_t* __restrict__ parts = T.bins;
   const int qi_ = blockIdx.x, c = threadIdx.x, lane = c & 31, warp = c >> 5;
+  const unsigned long long empty_bits = (unsigned long long)__double_as_longlong(kEmptyDist);
   if (c == 0) {
     s_n = 0;
     s_tie = 0;
@@ -687,31 +758,49 @@ __global__ void __launch_bounds__(KB)
     }
   }
   if (ncand > 0) hi = U;
-  s_iv[c] = make_double2(lo, hi);
+  // non-negative doubles order like their bit patterns
+  const unsigned long long lo_b = (unsigned long long)__double_as_longlong(lo);
+  const unsigned long long hi_b = (unsigned long long)__double_as_longlong(hi);
+  s_key[c] = lo_b;
+  s_val[c] = c;
+  s_hi[c] = hi_b;
+  __syncthreads();
+  bitonic_sort_512(s_key, s_val, c);             // by interval start
+  // running maximum of the interval ends in sorted order (Hillis-Steele)
+  unsigned long long pm = s_hi[s_val[c]];
+  const unsigned long long my_hi_sorted = pm;
+  __syncthreads();
+  s_pm[c] = pm;
+  __syncthreads();
+  for (int o = 1; o < KB; o <<= 1) {
+    const unsigned long long prev = c >= o ? s_pm[c - o] : 0ull;
+    __syncthreads();
+    pm = prev > pm ? prev : pm;
+    s_pm[c] = pm;
+    __syncthreads();
+  }
+  {
+    // sorted position c: does this bin's interval touch another one?  (empty bins sort last and touch nothing)
+    const bool nonempty = my_hi_sorted < empty_bits;
+    const bool right = c + 1 < KB && s_key[c + 1] <= my_hi_sorted;
+    const bool left = c > 0 && s_pm[c - 1] >= s_key[c];
+    s_ov[s_val[c]] = nonempty && (left || right);
+  }
   __syncthreads();
   // a bin needs a float64 decision when several shards could hold its winner, or when its interval overlaps
   // another bin's (the rank transform would be undecided); exact points need nothing
-  bool need = ncand > 1;
-  if (ncand == 1 && !(exact && lo == hi)) {
-    int ov = 0;
-#pragma unroll 8
-    for (int j = 0; j < KB; ++j) {
-      const double2 o = s_iv[j];
-      ov += (o.x <= hi) & (lo <= o.y) & (o.y < kEmptyDist);
-    }
-    need = ov > 1;                              // the bin always overlaps itself
-  }
+  const bool need = ncand > 1 || (ncand == 1 && s_ov[c] && !(exact && lo == hi));
   if (need) s_list[atomicAdd(&s_n, 1)] = c;
-  __syncthreads();
-  const int n_list = s_n;
   s_id[c] = id;
   s_d[c] = (unsigned long long)__double_as_longlong(ncand >= 1 ? 0.5 * (lo + hi) : kEmptyDist);
+  s_hi[c] = hi_b;                                 // by code again (the verify loop reads U of a bin)
   __syncthreads();
+  const int n_list = s_n;
   const qpg_qinfo_t qi = T.q_info[qi_];
   const float* qrow = T.q + (size_t)qi_ * T.ldq;
   for (int it = warp; it < n_list; it += KB / 32) {
     const int cc = s_list[it];
-    const double Uc = s_iv[cc].y;
+    const double Uc = __longlong_as_double((long long)s_hi[cc]);
     double bd = 1e300;
     long long bid = -1;
     for (int p = 0; p < P; ++p) {
@@ -736,22 +825,22 @@ __global__ void __launch_bounds__(KB)
   }
   __syncthreads();
   if (c == 0 && stats) atomicAdd(&stats[1], (unsigned long long)n_list);
-  // stable rank (ties -> lower code first) + tie flag among non-empty bins
+  // stable rank (ties -> lower code first) = position in the order by (distance, code); tie flag among non-empty bins
   const unsigned long long mine = s_d[c];
-  const unsigned long long empty_bits = (unsigned long long)__double_as_longlong(kEmptyDist);
-  int r = 0, tie = 0;
-#pragma unroll 8
-  for (int j = 0; j < KB; ++j) {
-    const unsigned long long o = s_d[j];
-    r += (o < mine) || (o == mine && j < c);
-    tie |= (o == mine && j != c && mine != empty_bits);
+  s_key[c] = mine;
+  s_val[c] = c;
+  __syncthreads();
+  bitonic_sort_512(s_key, s_val, c);
+  {
+    const unsigned long long k = s_key[c];
+    const bool tie = k != empty_bits && ((c + 1 < KB && s_key[c + 1] == k) || (c > 0 && s_key[c - 1] == k));
+    if (tie) s_tie = 1;
+    T.ranks[(size_t)qi_ * KB + s_val[c]] = c;
   }
-  if (tie) s_tie = 1;
   Pair out;
   out.d = mine;
   out.id = (unsigned long long)s_id[c];
   T.table[(size_t)qi_ * KB + c] = out;
-  T.ranks[(size_t)qi_ * KB + c] = r;
   __syncthreads();
   if (c == 0 && T.qflags) T.qflags[qi_] = s_tie;
 }
@@ -912,7 +1001,7 @@ extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64
   const int rc = fill_tables(tabs, n_tabs, true, &tp);
   if (rc != QPG_OK) return rc;
   const long long Wpad = (W + TM - 1) / TM * TM;
-  const long long warps = (long long)nq * KB;
+  const long long warps = (long long)((nq + BG - 1) / BG) * KB;
   const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);
   sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
                                                              reinterpret_cast<unsigned long long*>(stats));
