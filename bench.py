@@ -1,26 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- seconds-of-audio matched per second on the phase-guided matcher.
 
-Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON
-line from rank 0.  For N > 1 it is launched under torch.distributed.run, one rank
-per GPU (NCCL).  `--impl reference` times the reference's CPU algorithm (the
-oracle port with the reference's per-window loop) on the host cores instead.
+Contract (driver): `python bench.py --gpus N --steps K --warmup W` prints ONE JSON line from rank 0.  For N > 1
+it is launched under torch.distributed.run, one rank per GPU (NCCL).  `--impl reference` times the reference's
+CPU algorithm on the host cores instead (the reference itself through oracle/ref_harness.py when
+/root/reference is present, else the oracle port with the reference's per-window loop).
 
-Workload "speaker10_24s" (BASELINE.json configs[2]): synthetic speaker-10-like
-database, N_seq = 512 sequences = 13 312 candidate windows, stacked WavLM
-feature 6 x 1024 = 6144-d + 384-d text context, one 24-s query clip (6 segments
-= 48 query steps) PER GPU.  With N GPUs the database rows are sharded N ways,
-every rank scans its shard for all N clips, the per-shard [48N, 512] tables are
-merged with one NCCL all-gather + a min-merge kernel, and each rank runs the
-sequential tail of its own clip: per-GPU work is constant -> "scaling": "weak".
+Headline workload "speaker10_24s" (BASELINE.json configs[2]): synthetic speaker-10-like database, 512
+sequences = 13 312 candidate windows, stacked WavLM feature 6 x 1024 = 6144-d + 384-d text context, one 24-s
+query clip (6 segments = 48 query steps) PER GPU.  The 0.7 GB database is replicated on every GPU and the clips
+are split (weak scaling, no data-path collective): cutting a table this small would only multiply fixed costs.
 
-A step = one pass of the hot path over one batch of clips:
+A step = one pass of the hot path over one batch of clips (one CUDA-graph replay: query slicing, ONE int8
+tensor-core pass over the sliced table for all 48 steps, interval records, float64 decisions, rank transform,
+lookup, transitions, walk):
   value : queries already resident in HBM when the timed region starts
-  e2e   : through CodeKNN.match_clips-equivalent host path, pinned host query
-          buffers -> H2D, kernels, D2H of the int64 codes, all inside the timing
-Inputs (347 MB of windows) are larger than the 126 MB L2 and every pass streams
-all of them, so no explicit L2 flush is needed between iterations.
-"""
+  e2e   : through CodeKNN.match_clips - pinned host queries -> H2D, the captured step, D2H of codes + status
+The table (348 MB) is larger than the 126 MB L2 and every step streams all of it, so no explicit L2 flush is
+needed between iterations.
+
+Row-sharded workloads (`sharded` sub-records; BASELINE.json configs[3] and [4]) run after the headline
+measurement: the all-speaker-like 852k x 6528 table with 64 clips, and the 1M x 512-d sweep with 8 queries;
+rows sharded over the N ranks, ONE all-gather of the per-bin records, strong scaling."""
 from __future__ import annotations
 
 import argparse
@@ -47,19 +48,21 @@ def parse():
     p.add_argument("--steps", type=int, default=20)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", choices=("ours", "reference"), default="ours")
-    p.add_argument("--workload", choices=("speaker10_24s", "allspeaker"), default="speaker10_24s",
-                   help="allspeaker: 32 768 sequences (852k windows, 22 GB) generated on the device, 8 clips, strong scaling")
     p.add_argument("--n-seq", type=int, default=512)
     p.add_argument("--wavlm-dim", type=int, default=1024)
     p.add_argument("--ctx-dim", type=int, default=384)
     p.add_argument("--clips-per-gpu", type=int, default=1)
+    p.add_argument("--engine", choices=("sliced", "f64"), default="sliced",
+                   help="f64 = the float64 streaming scans of round 1 (4 steps per pass)")
     p.add_argument("--cpu-sample-seq", type=int, default=32, help="database sequences in the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--row-shards", type=int, default=0, help="0 = plan_layout() decides")
     p.add_argument("--no-vqvae", action="store_true", help="skip the informational VQ-VAE block")
+    p.add_argument("--no-parity", action="store_true", help="skip the oracle check of the benchmarked workload")
+    p.add_argument("--no-sharded", action="store_true", help="skip the row-sharded sub-records")
+    p.add_argument("--sharded-n-seq", type=int, default=32768, help="sequences of the all-speaker-like table")
+    p.add_argument("--sharded-clips", type=int, default=64)
+    p.add_argument("--sweep-windows", type=int, default=1 << 20)
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
-    p.add_argument("--no-fused", action="store_true", help="separate audio and text scans instead of the fused pass")
-    p.add_argument("--overlap", action="store_true", help="overlap the sequential tail with the scans (side stream)")
     return p.parse_args()
 
 
@@ -74,27 +77,28 @@ def make_database_arrays(n_seq, wavlm_dim, ctx_dim, seed=0):
     aud_rows = dp.wavlm_window_rows(dp.interpolate_wavlm(train["wavlm"]))
     txt_rows = np.ascontiguousarray(train["context"].squeeze(2)[:, :26, :].reshape(n_seq * 26, -1))
     return dict(code=code, signature=sig, phase_amp=phase_to_dense(train["phase"]), aud_rows=aud_rows,
-                txt_rows=txt_rows, train=train)
+                txt_rows=txt_rows)
 
 
-def make_database_on_device(n_seq, wavlm_dim, ctx_dim, j0, j1, dev, block=512):
-    """Large synthetic database generated on the GPU in 512-sequence blocks whose content depends only on
-    the block index, so every shard layout sees the same table.  Returns (small host arrays, audio rows of
-    sequences [j0, j1) on the device, text rows on the device)."""
+def make_database_on_device(n_seq, wavlm_dim, ctx_dim, dev, block=512):
+    """Large synthetic database generated on the GPU in 512-sequence blocks whose content depends only on the
+    block index, so every rank sees the same table.  Returns (small host arrays, audio rows, text rows)."""
     import torch
 
     rng = np.random.default_rng(0)
     code = rng.integers(0, 512, size=(n_seq, 30)).astype(np.int64)
     signature = rng.standard_normal((512, 135)).astype(np.float32)
     phase_amp = rng.standard_normal((n_seq, 240, 16)).astype(np.float32)
-    assert j0 % block == 0 and j1 % block == 0, "shards must be multiples of 512 sequences"
-    aud, txt = [], []
+    assert n_seq % block == 0
+    aud = torch.empty((n_seq * 26, 6 * wavlm_dim), dtype=torch.float32, device=dev)
+    txt = torch.empty((n_seq * 26, ctx_dim), dtype=torch.float32, device=dev)
     g = torch.Generator(device=dev)
-    for blk in range(j0 // block, j1 // block):
+    for blk in range(n_seq // block):
         g.manual_seed(1000 + blk)
-        aud.append(torch.randn((block * 26, 6 * wavlm_dim), device=dev, generator=g))
-        txt.append(torch.randn((block * 26, ctx_dim), device=dev, generator=g))
-    return dict(code=code, signature=signature, phase_amp=phase_amp), torch.cat(aud), torch.cat(txt)
+        r0, r1 = blk * block * 26, (blk + 1) * block * 26
+        aud[r0:r1].normal_(generator=g)
+        txt[r0:r1].normal_(generator=g)
+    return dict(code=code, signature=signature, phase_amp=phase_amp), aud, txt
 
 
 def make_clip_queries(n_clips, wavlm_dim, ctx_dim, seed=1000):
@@ -105,7 +109,19 @@ def make_clip_queries(n_clips, wavlm_dim, ctx_dim, seed=1000):
     ctx = rng.standard_normal((n_clips * N_SEG, 30, ctx_dim)).astype(np.float32)
     aq = dp.wavlm_query_rows(dp.interpolate_wavlm(wav)).reshape(n_clips, N_SEG, 8, -1)
     tq = ctx[:, [int(24 * s / 180 * 30) for s in range(8)], :].reshape(n_clips, N_SEG, 8, -1)
-    return np.ascontiguousarray(aq), np.ascontiguousarray(tq), wav, ctx
+    return np.ascontiguousarray(aq), np.ascontiguousarray(tq)
+
+
+def make_seeds(n_clips, code, phase_amp, n_seq):
+    """init_code_phase (GestureKNN.py:462-473) for every clip from one legacy RandomState(123456)"""
+    rs = np.random.RandomState(123456)
+    sc, sp = [], []
+    for _ in range(n_clips):
+        i0 = rs.randint(0, n_seq)
+        j0 = rs.randint(0, 180 - 8)
+        sc.append(int(code[i0, j0 // 30]))
+        sp.append(phase_amp[i0, j0:j0 + 8])
+    return np.array(sc, dtype=np.int32), np.stack(sp).astype(np.float32)
 
 
 # ------------------------------------------------------------------ clocks
@@ -160,34 +176,59 @@ class ClockSampler:
         return out
 
 
-# ------------------------------------------------------------------ CPU baseline (oracle port)
+# ------------------------------------------------------------------ CPU baseline / reference arm
 def cpu_baseline(args, n_sample_seq, n_segments=1):
-    """The reference's algorithm with its own cost structure (one scikit-learn call per
-    window and step, single thread) on a bounded sample: `n_sample_seq` database
-    sequences, `n_segments` 4-s segments; cost is linear in the number of sequences
-    (BASELINE.md section 2), so the figure is scaled to args.n_seq."""
+    """The reference's algorithm with its own cost structure (one scikit-learn call per window and step, single
+    thread) on a bounded sample: `n_sample_seq` database sequences, `n_segments` 4-s segments; cost is linear in
+    the number of sequences, so the figure is scaled to args.n_seq.  When the reference
+    tree is present (build container) its own CodeKNN.search_code_knn is what runs (kind "reference")."""
     from oracle import matcher_np as om
+    from oracle import ref_harness
     from qpgesture_b200 import synth
     from sklearn.metrics.pairwise import paired_distances  # noqa: F401  (import outside the timing)
 
     train, test, code, sig = synth.make_arrays(n_sample_seq, n_segments, seed=0, wavlm_dim=args.wavlm_dim,
                                                ctx_dim=args.ctx_dim)
+    scale = args.n_seq / n_sample_seq
+    audio_s = SEG_SECONDS * n_segments
+    kind, t_loop, t_vec = "port", None, None
+    if ref_harness.available():
+        import tempfile
+        try:
+            with tempfile.TemporaryDirectory() as root:
+                p = synth.write_npz_set(root, train, test, code, sig, object_phase=True)
+                mod, knn, q = ref_harness.build_codeknn(p.as_argv(os.path.join(root, "o.npz"), max_frames=0), mode="A")
+                np.random.seed(123456)
+                with ref_harness._quiet():                 # the reference prints its progress to stdout
+                    t0 = time.perf_counter()
+                    prev = None
+                    for i in range(n_segments):
+                        prev = knn.search_code_knn(clip_test=q["test_wavlm_feat"][i], desired_k=0, use_wavlm=True,
+                                                   use_feature=True, use_freq=False,
+                                                   seed_code=None if prev is None else prev[0][-1], use_wavvq=False,
+                                                   use_phase=True, seed_phase=None if prev is None else prev[1][-1],
+                                                   use_txt=True, clip_context=q["test_context"][i], use_aud=True)
+                    t_loop = time.perf_counter() - t0
+                ref_harness.release_gestureknn()
+                kind = "reference"
+        except Exception as e:  # noqa: BLE001  (fall back to the port, say why)
+            print(f"[bench] reference run failed ({type(e).__name__}: {e}); timing the oracle port", file=sys.stderr)
     db = om.build_db("A", code, sig, train["phase"], train["context"], wavlm=train["wavlm"])
     aq, tq = om.build_queries("A", test["context"], test_wavlm=test["wavlm"])
     seed = om.init_code_phase(db, np.random.RandomState(123456))
-    om.scan_loop(db.txt_rows[:26], db.labels[:26], tq[0, 0])          # warm caches / imports
-    t0 = time.perf_counter()
-    om.predict_codes_loop(db, aq, tq, seed)
-    t_loop = time.perf_counter() - t0
+    if t_loop is None:
+        om.scan_loop(db.txt_rows[:26], db.labels[:26], tq[0, 0])          # warm caches / imports
+        t0 = time.perf_counter()
+        om.predict_codes_loop(db, aq, tq, seed)
+        t_loop = time.perf_counter() - t0
     t0 = time.perf_counter()
     om.predict_codes(db, aq, tq, seed=seed)
     t_vec = time.perf_counter() - t0
-    scale = args.n_seq / n_sample_seq
-    audio_s = SEG_SECONDS * n_segments
-    return dict(value=audio_s / (t_loop * scale), unit="s_audio/s", cores=1, kind="port",
-                sample=(f"{n_segments} x 4-s segment against {n_sample_seq} of {args.n_seq} database sequences, "
-                        f"per-window sklearn loop as GestureKNN.py:671-690; {t_loop:.2f} s measured, scaled x{scale:g} "
-                        "(cost linear in sequences)"),
+    what = ("the reference's own CodeKNN.search_code_knn (GestureKNN.py:501-664, imported in place)" if kind == "reference"
+            else "oracle port with the reference's per-window sklearn loop (GestureKNN.py:671-690)")
+    return dict(value=audio_s / (t_loop * scale), unit="s_audio/s", cores=1, kind=kind, extrapolated=True, scale=scale,
+                sample=(f"{n_segments} x 4-s segment against {n_sample_seq} of {args.n_seq} database sequences, {what}; "
+                        f"{t_loop:.2f} s measured, scaled x{scale:g} (cost linear in sequences)"),
                 vectorised_value=audio_s / (t_vec * scale), host_cores=os.cpu_count())
 
 
@@ -196,17 +237,23 @@ def run_reference_arm(args):
     if rank != 0:
         return
     vals = []
+    n_sample = args.cpu_sample_seq                       # default 32 sequences x 1 segment
     for i in range(args.warmup + args.steps):
-        r = cpu_baseline(args, args.cpu_sample_seq if args.cpu_sample_seq <= 8 else 8, 1)
+        r = cpu_baseline(args, n_sample, 1)
         if i >= args.warmup:
             vals.append(r)
+        if i == 0 and r["value"] > 0:                  # keep the whole run within a few minutes
+            per_step = SEG_SECONDS / (r["value"] * r["scale"]) * 1.3
+            budget_steps = max(1, int(150.0 / max(per_step, 1e-3)))
+            if args.warmup + args.steps > budget_steps:
+                args.steps = max(1, budget_steps - args.warmup)
     v = statistics.mean(x["value"] for x in vals)
-    base = vals[-1]
+    base = dict(vals[-1])
     base["value"] = v
     line = dict(metric="seconds_of_audio_matched_per_second", value=v, unit="s_audio/s", n_gpus=args.gpus,
-                steps=args.steps, warmup=args.warmup, ms_per_step=1e3 * SEG_SECONDS * N_SEG / v,
+                steps=len(vals), warmup=args.warmup, ms_per_step=1e3 * SEG_SECONDS * N_SEG / v,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                impl="reference",
+                impl="reference", extrapolated=True, scale=base["scale"],
                 config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
                             audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu),
                 cpu_baseline=base,
@@ -240,7 +287,7 @@ def vqvae_block(dev, B=4096, T=8):
             zs = m.encode(x)
         e1.record()
         for _ in range(reps):
-            y = m.decode(zs)
+            m.decode(zs)
         e2.record()
         torch.cuda.synchronize()
         enc_ms, dec_ms = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
@@ -248,9 +295,227 @@ def vqvae_block(dev, B=4096, T=8):
         out[name] = dict(encode_ms=enc_ms, decode_ms=dec_ms, codes_per_s=B * T / 8 / enc_ms * 1e3,
                          decoded_frames_per_s=B * T / dec_ms * 1e3,
                          encode_tflops=1.6235 * B * T / 240 / enc_ms, decode_tflops=1.9083 * B * T / 240 / dec_ms)
-    out["index_agreement_tf32_vs_fp32"] = float((codes["tf32_tcgen05"] == codes["fp32_ffma"]).float().mean())
+    neq = int((codes["tf32_tcgen05"] != codes["fp32_ffma"]).sum())
+    out["index_mismatches_tf32_vs_fp32"] = neq
+    out["index_agreement_tf32_vs_fp32"] = 1.0 - neq / codes["fp32_ffma"].numel()
     out["shape"] = [B, T, 135]
     return out
+
+
+# ------------------------------------------------------------------ helpers
+def timed_steps(fn, steps, warmup, dev, world):
+    import torch
+    import torch.distributed as dist
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
+def oracle_parity(arrs, aq, tq, seed_code, seed_phase, plan, knn):
+    """The benchmarked workload against the oracle (test infrastructure, outside every timed region): the
+    48 x 512 audio and text tables via sklearn's own paired cosine distance over ALL windows, and the codes via
+    the oracle's sequential tail (stable tie order, this machine's frequency ranks)."""
+    from oracle import matcher_np as om
+    from qpgesture_b200.matchdb import table_to_numpy
+
+    t0 = time.perf_counter()
+    code = arrs["code"]
+    labels = code[:, :26].reshape(-1).astype(np.int64)
+    odb = om.OracleDB(mode="A", code=code, labels=labels, aud_rows=arrs["aud_rows"].astype(np.float64),
+                      txt_rows=arrs["txt_rows"], aud_k=np.arange(26) * 6, txt_k=np.arange(26) * 8,
+                      phase_amp=arrs["phase_amp"], signature=np.asarray(arrs["signature"]),
+                      freq_dist=om.code_to_freq(code), n_db_frm=180, step_sz=6)
+    ta, tt = table_to_numpy(plan.ta), table_to_numpy(plan.tt)
+    n_seg = aq.shape[0]
+    mism = dict(audio=0, text=0)
+    max_dd = 0.0
+    tables = []
+    for g in range(n_seg):
+        at = [om.audio_table(odb, aq[g, s].astype(np.float64)) for s in range(8)]
+        xt = [om.text_table(odb, tq[g, s]) for s in range(8)]
+        tables.append((at, xt))
+        for s in range(8):
+            i = g * 8 + s
+            mism["audio"] += int((ta[i]["id"] != at[s][1]).sum())
+            mism["text"] += int((tt[i]["id"] != xt[s][1]).sum())
+            max_dd = max(max_dd, float(np.abs(ta[i]["d"] - at[s][0]).max()), float(np.abs(tt[i]["d"] - xt[s][0]).max()))
+    want = om.predict_codes(odb, aq, tq, ties="stable", seed=(int(seed_code), seed_phase), tables=tables,
+                            freq_score=knn.db.freq_rank_host)
+    got = plan.codes[0].cpu().numpy()
+    return dict(codes_equal=bool(np.array_equal(got, want)), table_id_mismatches=mism["audio"] + mism["text"],
+                table_id_mismatches_audio=mism["audio"], table_id_mismatches_text=mism["text"],
+                max_table_distance_diff=max_dd, steps_checked=n_seg * 8, windows=int(labels.size),
+                oracle="oracle/matcher_np.py audio_table/text_table (sklearn paired cosine, float64 audio / float32 "
+                       "text as the reference) + predict_codes(ties='stable')",
+                seconds=round(time.perf_counter() - t0, 1))
+
+
+# ------------------------------------------------------------------ row-sharded sub-records
+def sharded_allspeaker(args, dev, world, rank, pg_world, peak):
+    """BASELINE.json configs[3]: 64 clips x all-speaker-like table (32 768 sequences = 851 968 windows x 6528-d,
+    22 GB float32), rows sharded over the ranks, ONE all-gather of the per-bin records per step.  The float32
+    copy is replicated (it is only touched to settle undecided bins), the scanned int8-sliced copy is sharded."""
+    import torch
+    import torch.distributed as dist
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.GestureKNN import CodeKNN
+    from qpgesture_b200.matchdb import MatchDatabase
+    from qpgesture_b200.sharding import shard_sequences
+
+    n_seq, n_clips = args.sharded_n_seq, args.sharded_clips
+    assert n_clips % world == 0
+    t0 = time.perf_counter()
+    arrs, aud, txt = make_database_on_device(n_seq, args.wavlm_dim, args.ctx_dim, dev)
+    j0, j1 = shard_sequences(n_seq, world, rank)
+    db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], txt, aud_rows=aud, device=dev,
+                       seq_range=(j0, j1) if world > 1 else None, replicate_exact=world > 1)
+    del aud, txt
+    torch.cuda.empty_cache()
+    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg_world, tail="device")
+    per = n_clips // world
+    my = slice(rank * per, (rank + 1) * per)
+    plan = knn.make_plan(n_clips, N_SEG, tail_clips=my, use_graph=False)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4242)                                   # same queries on every rank
+    plan.qa.copy_(torch.randn(plan.qa.shape, device=dev, generator=g))
+    plan.qt.copy_(torch.randn(plan.qt.shape, device=dev, generator=g))
+    sc, sp = make_seeds(n_clips, arrs["code"], arrs["phase_amp"], n_seq)
+    plan.seed_code.copy_(torch.from_numpy(sc))
+    plan.seed_phase.copy_(torch.from_numpy(sp))
+    build_s = time.perf_counter() - t0
+    steps = 3
+    ms = timed_steps(lambda: knn.run_plan(plan), steps, 1, dev, world)
+    status = plan.status.cpu().numpy()
+    # one scan pass alone (the dominant kernel) and the collective alone
+    lib = _lib.load()
+    ps = plan.passes[0]
+    A, T = db.aud_s, db.txt_s
+    segs = (_lib.SlicedSeg * 2)()
+    segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.data_ptr(), ps.qs_a.data_ptr(), plan.sacc_a.data_ptr(), A.n_kblocks
+    segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), plan.sacc_t.data_ptr(), T.n_kblocks
+    sp_ = _lib.stream_ptr()
+    pass_ms = timed_steps(lambda: lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp_), 5, 2, dev, world)
+    plan.sacc_a.zero_()
+    plan.sacc_t.zero_()
+    coll_ms = 0.0
+    if world > 1:
+        if plan.exchange == "all_to_all":
+            coll_ms = timed_steps(lambda: dist.all_to_all_single(plan.parts, plan.bins, group=pg_world), 5, 2, dev, world)
+        else:
+            coll_ms = timed_steps(lambda: dist.all_gather_into_tensor(plan.parts, plan.bins, group=pg_world), 5, 2, dev, world)
+    # property check at full size: a clip whose queries are database windows finds them (distance 0) - done on
+    # the tables of this rank's clips
+    audio_seconds = n_clips * N_SEG * SEG_SECONDS
+    shard_bytes = A.W * (4 * (db.aud.D + db.txt.D) + 4)
+    rec = dict(workload="allspeaker_64clips", n_seq=n_seq, windows=n_seq * 26, clips=n_clips,
+               query_steps=n_clips * N_SEG * 8, row_shards=world, passes_per_step=len(plan.passes), steps=steps,
+               ms_per_step=ms, value=audio_seconds / (ms * 1e-3), unit="s_audio/s", scaling="strong",
+               collective=(f"one {plan.exchange} of per-bin records (32 B x 2 tables x 512 codes per query step); every rank "
+                           "receives the records of its own clips only") if world > 1 else None,
+               collective_bytes_received_per_rank=int(plan.parts.numel() * 8) if world > 1 else 0, collective_ms=coll_ms,
+               scan_pass_ms=pass_ms, scan_GBps_per_gpu=shard_bytes / (pass_ms * 1e-3) / 1e9,
+               scan_frac_of_hbm_peak=shard_bytes / (pass_ms * 1e-3) / 1e9 / peak,
+               status_ok=bool((status & 1).max() == 0), build_seconds=round(build_s, 1),
+               float64_decisions_per_step=int(plan.stats.cpu()[1]) // (steps + 1))
+    del plan, knn, db
+    torch.cuda.empty_cache()
+    return rec
+
+
+def sharded_sweep(args, dev, world, rank, pg_world, peak):
+    """BASELINE.json configs[4]: independent windows db ~ N(0,1) [W, 512], labels ~ U{0..511}, 8 queries; rows
+    sharded over the ranks; scan -> per-bin records -> ONE all-gather -> resolve.  Checked against the float64
+    scan kernel over the whole table on every rank."""
+    import torch
+    import torch.distributed as dist
+    from qpgesture_b200 import _lib
+    from qpgesture_b200.matchdb import PackedRows, SlicedRows, aligned_bytes, bin_order, new_table
+
+    lib = _lib.load()
+    W = (args.sweep_windows // (128 * world)) * 128 * world
+    D, Q, n_pad = 512, 8, 16
+    g = torch.Generator(device=dev)
+    g.manual_seed(7)
+    rows = torch.randn((W, D), device=dev, generator=g)
+    labels = torch.randint(0, 512, (W,), device=dev, dtype=torch.int32, generator=g)
+    q = torch.randn((Q, D), device=dev, generator=g)
+    pr = PackedRows.from_rows(rows)                       # replicated float32 table
+    w0, w1 = rank * W // world, (rank + 1) * W // world
+    order, bin_start = bin_order(labels[w0:w1])
+    S = SlicedRows.from_rows(rows[w0:w1], pr.sqnorm[w0:w1], order, bin_start)
+    qs = aligned_bytes(lib.qpg_sliced_query_bytes(D, n_pad), dev)
+    qinfo = torch.zeros((Q, 4), dtype=torch.float64, device=dev)
+    sacc = torch.zeros((n_pad, S.Wpad), dtype=torch.int64, device=dev)
+    bins = torch.zeros((Q, 512, 4), dtype=torch.int64, device=dev)
+    parts = bins[None] if world == 1 else torch.zeros((world, Q, 512, 4), dtype=torch.int64, device=dev)
+    tab, ranks = new_table(Q, dev), torch.zeros((Q, 512), dtype=torch.int32, device=dev)
+    job = (_lib.SliceJob * 1)()
+    job[0].q, job[0].col_exp, job[0].q_slices, job[0].q_info, job[0].ldq, job[0].D = \
+        _lib.dptr(q), _lib.dptr(S.col_exp), _lib.dptr(qs), _lib.dptr(qinfo), D, D
+    seg = (_lib.SlicedSeg * 1)()
+    seg[0].db_slices, seg[0].q_slices, seg[0].sacc, seg[0].n_kblocks = S.slices.data_ptr(), qs.data_ptr(), sacc.data_ptr(), S.n_kblocks
+    t = (_lib.SlicedTable * 1)()
+    t[0].packed, t[0].row_sqnorm, t[0].q, t[0].q_info, t[0].ldq, t[0].D = _lib.dptr(pr.packed), _lib.dptr(pr.sqnorm), _lib.dptr(q), _lib.dptr(qinfo), D, D
+    t[0].sacc, t[0].bin_start, t[0].row_info, t[0].order = _lib.dptr(sacc), _lib.dptr(S.bin_start), _lib.dptr(S.row_info), _lib.dptr(S.order)
+    t[0].bins, t[0].table, t[0].ranks = _lib.dptr(bins), _lib.dptr(tab), _lib.dptr(ranks)
+    tr = (_lib.SlicedTable * 1)()
+    tr[0].packed, tr[0].row_sqnorm, tr[0].q, tr[0].q_info, tr[0].ldq, tr[0].D = t[0].packed, t[0].row_sqnorm, t[0].q, t[0].q_info, D, D
+    tr[0].bins, tr[0].table, tr[0].ranks = _lib.dptr(parts), _lib.dptr(tab), _lib.dptr(ranks)
+    sp = _lib.stream_ptr()
+
+    def step():
+        _lib.check(lib.qpg_slice_queries_i8(job, 1, Q, n_pad, sp), "slice")
+        _lib.check(lib.qpg_sliced_scan_i8(seg, 1, S.W, n_pad, Q, sp), "scan")
+        _lib.check(lib.qpg_sliced_bins(t, 1, S.W, Q, w0, w0, 1, None, sp), "bins")
+        if world > 1:
+            dist.all_gather_into_tensor(parts, bins, group=pg_world)
+        _lib.check(lib.qpg_sliced_resolve(tr, 1, world, Q * 512, Q, 0, None, sp), "resolve")
+    gr = None
+    step()
+    torch.cuda.synchronize()
+    if world == 1:                                        # four launches: graph replay hides their launch cost
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr):
+            step()
+    run = (lambda: gr.replay()) if gr is not None else step
+    steps = 20
+    ms = timed_steps(run, steps, 3, dev, world)
+    pass_ms = timed_steps(lambda: lib.qpg_sliced_scan_i8(seg, 1, S.W, n_pad, Q, sp), 20, 3, dev, world)
+    sacc.zero_()
+    # exact float64 scan of the WHOLE table on this rank (round-1 kernel): ids must be identical
+    ref = new_table(Q, dev)
+    _lib.check(lib.qpg_table_init(_lib.ptr(ref), Q * 512, sp), "init")
+    _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(pr.packed), _lib.ptr(pr.sqnorm), _lib.ptr(labels), W, D, 0, _lib.ptr(q),
+                                             Q, _lib.ptr(ref), 0, sp), "f64 scan")
+    run()
+    torch.cuda.synchronize()
+    ids_equal = bool(torch.equal(tab[..., 1], ref[..., 1]))
+    shard_bytes = S.W * (4 * D + 4)
+    rec = dict(workload="sweep_1M_x_512", windows=W, dim=D, queries=Q, row_shards=world, steps=steps, ms_per_step=ms,
+               value=W * Q / (ms * 1e-3) / 1e9, unit="G window-queries/s", scaling="strong", cuda_graph=gr is not None,
+               scan_pass_ms=pass_ms, scan_GBps_per_gpu=shard_bytes / (pass_ms * 1e-3) / 1e9,
+               scan_frac_of_hbm_peak=shard_bytes / (pass_ms * 1e-3) / 1e9 / peak,
+               ids_equal_float64_scan=ids_equal,
+               collective="one all_gather_into_tensor of per-bin records" if world > 1 else None)
+    return rec
 
 
 # ------------------------------------------------------------------ our arm
@@ -265,7 +530,7 @@ def main():
 
     from qpgesture_b200 import _lib
     from qpgesture_b200.GestureKNN import CodeKNN
-    from qpgesture_b200.matchdb import MatchDatabase, new_table
+    from qpgesture_b200.matchdb import MatchDatabase
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -273,8 +538,8 @@ def main():
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world} (launch with torch.distributed.run)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    pg = None
     json_fd = None
+    pg_world = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL writes its version banner to stdout; the driver wants exactly ONE JSON line there.
@@ -283,81 +548,43 @@ def main():
         json_fd = os.dup(1)
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+        pg_world = dist.group.WORLD
     lib = _lib.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
 
-    # ---- layout: row shards x clip groups (qpgesture_b200/sharding.py: never cut a shard below the L2 size)
-    from qpgesture_b200.sharding import plan_layout, shard_sequences
-    if args.workload == "allspeaker" and args.n_seq == 512:
-        args.n_seq = 32768
-    db_bytes_total = args.n_seq * 26 * 4 * (6 * args.wavlm_dim + args.ctx_dim)
-    row_shards, clip_groups = plan_layout(db_bytes_total, world) if args.row_shards == 0 else \
-        (args.row_shards, world // args.row_shards)
-    assert row_shards * clip_groups == world
-    my_block, my_group = rank % row_shards, rank // row_shards
-    if row_shards > 1:
-        for gi in range(clip_groups):                      # every rank creates every group (NCCL requirement)
-            g_ = dist.new_group(list(range(gi * row_shards, (gi + 1) * row_shards)))
-            if gi == my_group:
-                pg = g_
-    else:
-        pg = None
-
-    # ---- database (one-off, outside every timed region)
-    j0, j1 = shard_sequences(args.n_seq, row_shards, my_block)
-    if args.workload == "allspeaker":
-        arrs, aud_dev, txt_dev = make_database_on_device(args.n_seq, args.wavlm_dim, args.ctx_dim, j0, j1, dev)
-        db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], txt_dev, aud_rows=aud_dev,
-                           device=dev, seq_range=(j0, j1))
-        del aud_dev, txt_dev
-        torch.cuda.empty_cache()
-    else:
-        arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
-        db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
-                           aud_rows=arrs["aud_rows"], device=dev, seq_range=(j0, j1))
-    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, process_group=pg)
-    strong = args.workload == "allspeaker"                 # fixed total work: 8 clips however many GPUs
-    n_clips_total = 8 if strong else args.clips_per_gpu * world
-    if strong:
-        assert n_clips_total % clip_groups == 0 and (n_clips_total // clip_groups) % row_shards == 0
-        args.clips_per_gpu = n_clips_total // world
-    n_clips = args.clips_per_gpu * row_shards              # clips this rank's row group scans together
-    aq_all, tq_all, _, _ = make_clip_queries(n_clips_total, args.wavlm_dim, args.ctx_dim)
-    g_lo = my_group * n_clips
-    aq, tq = aq_all[g_lo:g_lo + n_clips], tq_all[g_lo:g_lo + n_clips]
+    # ---- headline workload: database replicated, clips split (one-off set-up, outside every timed region)
+    arrs = make_database_arrays(args.n_seq, args.wavlm_dim, args.ctx_dim)
+    db = MatchDatabase("A", arrs["code"], arrs["signature"], arrs["phase_amp"], arrs["txt_rows"],
+                       aud_rows=arrs["aud_rows"], device=dev)
+    knn = CodeKNN(database=db, use_wavlm=True, use_phase=True, use_txt=True, tail="device")
+    n_clips = args.clips_per_gpu
+    n_clips_total = n_clips * world
+    aq_all, tq_all = make_clip_queries(n_clips_total, args.wavlm_dim, args.ctx_dim)
+    sc_all, sp_all = make_seeds(n_clips_total, arrs["code"], arrs["phase_amp"], args.n_seq)
+    lo = rank * n_clips
+    aq, tq = aq_all[lo:lo + n_clips], tq_all[lo:lo + n_clips]
     Q = n_clips * N_SEG * 8
-    seed_rng = np.random.RandomState(123456)
-    seeds = []
-    for _ in range(n_clips_total):
-        i0 = seed_rng.randint(0, args.n_seq)
-        j0_ = seed_rng.randint(0, 180 - 8)
-        seeds.append((int(arrs["code"][i0, j0_ // 30]), arrs["phase_amp"][i0, j0_:j0_ + 8]))
-    seeds = seeds[g_lo:g_lo + n_clips]
-    seed_code = np.array([s[0] for s in seeds], dtype=np.int32)
-    seed_phase = np.stack([s[1] for s in seeds]).astype(np.float32)
-    my_clips = slice(my_block * args.clips_per_gpu, (my_block + 1) * args.clips_per_gpu)
-
     aq_h = torch.from_numpy(aq.reshape(Q, -1)).pin_memory()
     tq_h = torch.from_numpy(tq.reshape(Q, -1)).pin_memory()
-    sc_h = torch.from_numpy(seed_code).pin_memory()
-    sp_h = torch.from_numpy(seed_phase).pin_memory()
-    codes_h = torch.empty((args.clips_per_gpu, N_SEG, 30), dtype=torch.int64).pin_memory()
-    # the whole step (2 table inits, all scan passes, [all-gather + merge], 2 rank kernels, tail) is a fixed
-    # launch sequence over static buffers; by default it is captured once into a CUDA graph and replayed
+    sc_h = torch.from_numpy(sc_all[lo:lo + n_clips].copy()).pin_memory()
+    sp_h = torch.from_numpy(sp_all[lo:lo + n_clips].copy()).pin_memory()
+    codes_h = torch.empty((n_clips, N_SEG, 30), dtype=torch.int64).pin_memory()
+    status_h = torch.zeros((n_clips,), dtype=torch.int32).pin_memory()
     use_graph = not args.no_graph
-    try:
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=use_graph,
-                             overlap_tail=args.overlap, fused_scan=not args.no_fused)
-    except Exception as e:                                   # e.g. NCCL capture unsupported: plain launches
-        if rank == 0:
-            print(f"[bench] graph capture failed ({type(e).__name__}: {e}); using plain launches", file=sys.stderr)
-        use_graph = False
-        plan = knn.make_plan(n_clips, N_SEG, tail_clips=my_clips, use_graph=False, overlap_tail=args.overlap, fused_scan=not args.no_fused)
-    knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, (my_clips.start, my_clips.stop))] = plan
+    plan = knn.make_plan(n_clips, N_SEG, use_graph=use_graph, engine=args.engine)
+    knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, None, None)] = plan        # match_clips reuses this plan
     plan.qa.copy_(aq_h)
     plan.qt.copy_(tq_h)
     plan.seed_code.copy_(sc_h)
     plan.seed_phase.copy_(sp_h)
     torch.cuda.synchronize()
+    if plan.engine == "sliced":
+        plan.stats.zero_()
     l0 = _lib.launch_count()
     knn._launch_plan(plan)                                   # count our kernels in one step (graphs hide them)
     torch.cuda.synchronize()
@@ -365,152 +592,140 @@ def main():
 
     def step_resident():
         knn.run_plan(plan)
-        return plan.codes, plan.status
 
-    aq4_h = aq_h.view(n_clips, N_SEG, 8, -1)
-    tq4_h = tq_h.view(n_clips, N_SEG, 8, -1)
+    aq4_h, tq4_h = aq_h.view(n_clips, N_SEG, 8, -1), tq_h.view(n_clips, N_SEG, 8, -1)
 
     def step_e2e():
-        # the public call a user makes (CodeKNN.match_clips): pinned host queries -> H2D, captured step, D2H codes
-        knn.match_clips(aq4_h, tq4_h, seed_code=sc_h, seed_phase=sp_h, out=codes_h, sync=False, tail_clips=my_clips)
-        return plan.codes, plan.status
-
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        l0 = _lib.launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
-            out = fn()
-        e1.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
-        launches = launches_per_step * steps
-        if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms / steps, launches, out
+        # the public call a user makes: pinned host queries -> H2D, captured step, D2H of codes and status
+        knn.match_clips(aq4_h, tq4_h, seed_code=sc_h, seed_phase=sp_h, out=codes_h, status_out=status_h, sync=False,
+                        tail="device")
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     warm = max(args.warmup, 3)                               # timing hygiene: never fewer than 3 warm-up steps
-    ms_res, launches, (codes, status) = timed(step_resident, args.steps, warm)
-    ms_e2e, _, _ = timed(step_e2e, args.steps, warm)
-    assert int(status.max().cpu()) == 0, "tail reported a start-code without window"
+    ms_res = timed_steps(step_resident, args.steps, warm, dev, world)
+    ms_e2e = timed_steps(step_e2e, args.steps, warm, dev, world)
+    assert int(status_h.max()) & 1 == 0, "a chosen start code had no window (IndexError in the reference)"
+    assert int(codes_h.min()) >= 0
 
-    # ---- dominant kernel alone: ONE pass (one launch) of the scan kernel the step actually uses
-    qpp_used = 4 if 6 * args.wavlm_dim > 2048 else 8
+    # ---- dominant kernel alone: ONE launch of the scan the step uses
     sp = _lib.stream_ptr()
-    if plan.fused:
-        qpp_used = 4
-        kernel_name = "cand_cosine2_kernel<QT=4,NCW=12> (audio|text fused pass)"
-        qf_small = plan.qf[:qpp_used].contiguous()
-        t1_small, t2_small = new_table(qpp_used, dev), new_table(qpp_used, dev)
-        alg_bytes = db.W * (4 * (db.aud.D + db.txt.D) + 4)
+    alg_bytes = db.W * (4 * (db.aud.D + db.txt.D) + 4)
+    if plan.engine == "sliced":
+        ps = plan.passes[0]
+        A, T = db.aud_s, db.txt_s
+        segs = (_lib.SlicedSeg * 2)()
+        segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.data_ptr(), ps.qs_a.data_ptr(), plan.sacc_a.data_ptr(), A.n_kblocks
+        segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), plan.sacc_t.data_ptr(), T.n_kblocks
+        kernel_name = f"sliced_scan_kernel (tcgen05 kind::i8, audio|text, {ps.nq} query steps per pass)"
+        queries_per_pass = ps.nq
 
         def one_pass():
-            _lib.check(lib.qpg_cand_cosine2_minbycode(_lib.ptr(db.fused.packed), _lib.ptr(db.aud.sqnorm),
-                                                      _lib.ptr(db.txt.sqnorm), _lib.ptr(db.labels), db.W, db.aud.D,
-                                                      db.txt.D, db.id_offset, _lib.ptr(qf_small), qpp_used,
-                                                      _lib.ptr(t1_small), _lib.ptr(t2_small), sp), "cosine2")
-        _lib.check(lib.qpg_table_init(_lib.ptr(t1_small), qpp_used * 512, sp), "init")
-        _lib.check(lib.qpg_table_init(_lib.ptr(t2_small), qpp_used * 512, sp), "init")
+            _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "scan")
     else:
-        kernel_name = f"cand_cosine_kernel<QT={qpp_used}> (audio pass)"
-        qa_small = plan.qa[:qpp_used].contiguous()
-        tab_small = new_table(qpp_used, dev)
-        t = db.aud
+        from qpgesture_b200.matchdb import new_table
+        queries_per_pass = 4
+        kernel_name = "cand_cosine_kernel<QT=4> (float64, audio pass)"
+        qa_small = plan.qa[:4].contiguous()
+        tab_small = new_table(4, dev)
         alg_bytes = db.algorithmic_bytes("audio")
+        _lib.check(lib.qpg_table_init(_lib.ptr(tab_small), 4 * 512, sp), "init")
 
         def one_pass():
-            _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(t.packed), _lib.ptr(t.sqnorm), _lib.ptr(db.labels), t.W,
-                                                     t.D, db.id_offset, _lib.ptr(qa_small), qpp_used,
-                                                     _lib.ptr(tab_small), qpp_used, sp), "cosine")
-        _lib.check(lib.qpg_table_init(_lib.ptr(tab_small), qpp_used * 512, sp), "init")
-    for _ in range(5):
-        one_pass()
-    torch.cuda.synchronize()
-    reps = 50
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(reps):
-        one_pass()
-    e1.record()
-    torch.cuda.synchronize()
-    pass_ms = e0.elapsed_time(e1) / reps
-    # The timed regions above last tens of milliseconds; keep the same step running for ~0.6 s more so that the
-    # 100 ms clock / throttle-reason sampler sees the device under exactly this load (not reported).  EVERY rank
-    # runs the same fixed number of steps (ms_res is already the max over ranks): in a row-sharded layout each
-    # step contains a collective, so a rank-0-only or wall-clock-bounded loop would deadlock.
-    soak_steps = min(2000, int(600.0 / max(ms_res, 1e-3)) + 1)
+            _lib.check(lib.qpg_cand_cosine_minbycode(_lib.ptr(db.aud.packed), _lib.ptr(db.aud.sqnorm), _lib.ptr(db.labels),
+                                                     db.aud.W, db.aud.D, db.exact_offset, _lib.ptr(qa_small), 4,
+                                                     _lib.ptr(tab_small), 4, sp), "cosine")
+    pass_ms = timed_steps(one_pass, 50, 5, dev, 1)
+    if plan.engine == "sliced":
+        plan.sacc_a.zero_()                                  # the timing loop accumulated into it
+        plan.sacc_t.zero_()
+    # keep the same step running ~0.6 s more so that the 100 ms clock / throttle-reason sampler sees the device
+    # under exactly this load.  Every rank runs the same fixed number of steps.
+    soak_steps = min(3000, int(600.0 / max(ms_res, 1e-3)) + 1)
     for _ in range(soak_steps):
         step_resident()
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
+    parity = None
+    if rank == 0 and not args.no_parity and n_clips == 1:
+        step_resident()
+        torch.cuda.synchronize()
+        parity = oracle_parity(arrs, aq[0], tq[0], sc_all[lo], sp_all[lo], plan, knn)
+
+    line = None
     if rank == 0:
-        peaks = {}
+        traffic, traffic_source = None, None
         try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None                                       # dram read+write per launch from the ncu --set full capture
-        try:
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r01_cosine_traffic.json")))
-            key = "fused" if plan.fused else "audio"
-            if tr[key]["W"] == db.W and tr[key]["D"] == (db.aud.D + db.txt.D if plan.fused else db.aud.D):
-                traffic = tr[key]["dram_bytes_per_launch"]
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r02_scan_traffic.json")))
+            if plan.engine == "sliced" and tr["W"] == db.W and tr["D"] == db.aud.D + db.txt.D:
+                traffic = tr["dram_bytes_per_launch"]
+                traffic_source = tr["source"]
         except Exception:
             pass
         achieved = alg_bytes / (pass_ms * 1e-3) / 1e9
         audio_seconds = n_clips_total * N_SEG * SEG_SECONDS
+        passes = len(plan.passes) if plan.engine == "sliced" else -(-Q // 4)
         line = dict(
             metric="seconds_of_audio_matched_per_second", value=audio_seconds / (ms_res * 1e-3), unit="s_audio/s",
             n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_res, higher_is_better=True,
-            scaling="strong" if strong else "weak", vs_baseline=None, dtype="f64", data="synthetic",
-            config=dict(workload=args.workload, n_seq=args.n_seq, windows=args.n_seq * 26,
-                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=args.clips_per_gpu, cuda_graph=bool(use_graph), tail_overlapped=bool(plan.overlap), fused_text_scan=bool(plan.fused),
-                        query_steps_per_rank_per_step=Q, db_bytes=int(db_bytes_total),
-                        parallelism=(f"{row_shards} row shards x {clip_groups} clip groups"
-                                     + (", all-gather + min-merge inside each row group" if row_shards > 1 else
-                                        ", database replicated, no data-path collective")) if world > 1
-                        else "single GPU",
-                        l2="inputs larger than L2 (no flush needed)" if db.aud.nbytes > 126e6 else
-                           "database shard fits L2; passes re-read it from L2"),
+            scaling="weak", vs_baseline=None,
+            dtype="s8 x s8 -> s32 exact integer filter (tcgen05) + f64 decisions" if plan.engine == "sliced" else "f64",
+            data="synthetic",
+            config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
+                        audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=n_clips, engine=plan.engine,
+                        cuda_graph=bool(use_graph), query_steps_per_rank_per_step=Q,
+                        db_bytes=int(db.W * 4 * (db.aud.D + db.txt.D)),
+                        parallelism=("database replicated, clips split, no data-path collective" if world > 1 else "single GPU"),
+                        l2="inputs larger than L2 (no flush needed)"),
+            passes_per_step=passes, queries_per_pass=queries_per_pass,
+            step_algorithmic_GBps=alg_bytes / (ms_res * 1e-3) / 1e9,
+            step_frac_of_hbm_peak=alg_bytes / (ms_res * 1e-3) / 1e9 / peak,
+            non_scan_ms_per_step=ms_res - passes * pass_ms,
             e2e=dict(value=audio_seconds / (ms_e2e * 1e-3), unit="s_audio/s", ms_per_step=ms_e2e,
                      h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4 + sc_h.numel() * 4 + sp_h.numel() * 4) * world,
-                     d2h_bytes_per_step=int(codes_h.numel() * 8) * world),
-            gpu_launches=int(launches),
-            roofline=dict(bound="hbm", kernel=kernel_name, achieved=achieved, peak=peak,
-                          unit="GB/s", frac=achieved / peak, traffic=traffic, launch_ms=pass_ms,
+                     d2h_bytes_per_step=int(codes_h.numel() * 8 + status_h.numel() * 4) * world),
+            gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
+            roofline=dict(bound="hbm", kernel=kernel_name, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                          traffic=traffic, traffic_source=traffic_source, launch_ms=pass_ms,
                           algorithmic_bytes=int(alg_bytes),
+                          algorithmic_bytes_definition="W*(4*(D_audio+D_text)+4), SURVEY.md 8(d) materialised windows",
                           peak_source="MEASURED_PEAKS.json" if peaks else "fallback (B200_PROFILING.md)"),
-            clocks=clocks,
+            clocks=clocks, parity=parity,
         )
-        if world == 1 and not args.no_vqvae:
-            line["vqvae"] = vqvae_block(dev)
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
+        if plan.engine == "sliced":
+            st = plan.stats.cpu().tolist()
+            line["float64_decisions"] = dict(rows_in_bins_stage=int(st[0]), bins_in_resolve_stage=int(st[1]),
+                                             steps_counted="all replays since the plan was reset")
+    del plan
+    torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_vqvae:
+        line["vqvae"] = vqvae_block(dev)
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
+    del knn, db
+    torch.cuda.empty_cache()
+    if not args.no_sharded and args.engine == "sliced":
+        sub = []
+        for fn in (sharded_sweep, sharded_allspeaker):
+            try:
+                rec = fn(args, dev, world, rank, pg_world, peak)
+            except Exception as e:  # noqa: BLE001  (a sub-record must not take the headline line down)
+                rec = dict(workload=fn.__name__, error=f"{type(e).__name__}: {e}")
+                if world > 1:
+                    raise
+            sub.append(rec)
+            torch.cuda.empty_cache()
+        if rank == 0:
+            line["sharded"] = sub
+    if rank == 0:
         if json_fd is not None:
             os.write(json_fd, (json.dumps(line) + "\n").encode())
         else:
             print(json.dumps(line))
     sys.stdout.flush()
     if world > 1:
-        # Tear down without touching the NCCL communicator that the captured graph references:
-        # destroy_process_group() after a graph-captured collective can block for minutes.
-        del plan
         torch.cuda.synchronize()
         dist.barrier()
         torch.cuda.synchronize()

@@ -167,7 +167,8 @@ typedef struct {
   const int32_t* bin_start;    /* bins: [513]                                                             */
   const void* row_info;        /* bins: from qpg_slice_rows_i8                                            */
   const int32_t* order;        /* bins: [W]                                                               */
-  qpg_bin_t* bins;             /* bins: out [nq][512];  resolve: in, part 0 (part p = + p*part_stride)    */
+  qpg_bin_t* bins;             /* bins: out;  resolve: in, part 0 (part p = + p*part_stride records);     */
+  int64_t bins_qstride;        /*   record of (query q, code c) at bins[q*bins_qstride + c]; 0 means 512    */
   qpg_pair_t* table;           /* resolve: out [nq][512]                                                  */
   int32_t* ranks;              /* resolve: out [nq][512]                                                  */
   int32_t* qflags;             /* resolve: out [nq] (may be NULL)                                         */

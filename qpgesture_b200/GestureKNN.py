@@ -339,9 +339,19 @@ class CodeKNN(object):
                 p.qinfo_t = torch.zeros((Q, 4), dtype=torch.float64, device=dev)
                 p.sacc_a = torch.zeros((n_pad_max, db.aud_s.Wpad), dtype=torch.int64, device=dev)
                 p.sacc_t = torch.zeros((n_pad_max, db.txt_s.Wpad), dtype=torch.int64, device=dev)
-                p.bins = torch.zeros((2, Q, codebook_size, 4), dtype=torch.int64, device=dev)      # qpg_bin_t, a then t
-                p.parts = p.bins[None] if world == 1 else \
-                    torch.zeros((world, 2, Q, codebook_size, 4), dtype=torch.int64, device=dev)
+                # per-bin records (qpg_bin_t, 32 bytes): [query][audio | text][code], so that the records of one rank's
+                # clips are one contiguous block.  Row shards exchange them with ONE collective: an all-to-all when
+                # the clips are split evenly (each rank receives only the records of its own clips), else an all-gather
+                p.bins = torch.zeros((Q, 2, codebook_size, 4), dtype=torch.int64, device=dev)
+                p.exchange = None
+                if world == 1:
+                    p.parts = p.bins[None]
+                else:
+                    import torch.distributed as dist
+                    r = dist.get_rank(self.process_group)
+                    even = n_clips % world == 0 and (tc.start, tc.stop) == (r * (n_clips // world), (r + 1) * (n_clips // world))
+                    p.exchange = "all_to_all" if even else "all_gather"
+                    p.parts = torch.zeros((world, Qt if even else Q, 2, codebook_size, 4), dtype=torch.int64, device=dev)
                 p.stats = torch.zeros((2,), dtype=torch.int64, device=dev)
                 p.ta, p.tt = new_table(Qt, dev), new_table(Qt, dev)
             else:
@@ -398,8 +408,8 @@ class CodeKNN(object):
             t.q, t.q_info, t.ldq, t.D = _lib.dptr(q[q0:q0 + nq]), _lib.dptr(qi[q0:q0 + nq]), E.D, E.D
             t.sacc, t.bin_start, t.row_info, t.order = _lib.dptr(sacc), _lib.dptr(S.bin_start), _lib.dptr(S.row_info), \
                 _lib.dptr(S.order)
-            t.bins = _lib.dptr(p.parts[0, x, bins_q0:bins_q0 + nq]) if for_resolve else \
-                _lib.dptr(p.bins[x, bins_q0:bins_q0 + nq])
+            t.bins = (p.parts[0, bins_q0, x] if for_resolve else p.bins[bins_q0, x]).data_ptr()
+            t.bins_qstride = 2 * codebook_size
             if for_resolve:
                 t.table, t.ranks, t.qflags = _lib.dptr(tab), _lib.dptr(rk), _lib.dptr(qf)
         return tabs
@@ -425,14 +435,19 @@ class CodeKNN(object):
             _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "qpg_sliced_scan_i8")
             _lib.check(lib.qpg_sliced_bins(self._sliced_tables(p, ps.q0, ps.nq, ps.q0), 2, A.W, ps.nq, db.id_offset,
                                            db.row_base, 1, _lib.ptr(p.stats), sp), "qpg_sliced_bins")
-        if p.world > 1:
-            import torch.distributed as dist
-            dist.all_gather_into_tensor(p.parts, p.bins, group=self.process_group)     # the ONE data-path collective
         per_clip = p.n_seg * STEPS_PER_SEGMENT
         q0, q1 = p.tail.start * per_clip, p.tail.stop * per_clip
-        stride = 2 * p.Q * codebook_size                                               # records between two parts
-        _lib.check(lib.qpg_sliced_resolve(self._sliced_tables(p, q0, q1 - q0, q0, for_resolve=True), 2, p.world, stride,
-                                          q1 - q0, db.exact_offset, _lib.ptr(p.stats), sp), "qpg_sliced_resolve")
+        part_q0 = q0
+        if p.world > 1:                                                               # the ONE data-path collective
+            import torch.distributed as dist
+            if p.exchange == "all_to_all":
+                dist.all_to_all_single(p.parts, p.bins, group=self.process_group)
+                part_q0 = 0                                                            # parts hold this rank's clips only
+            else:
+                dist.all_gather_into_tensor(p.parts, p.bins, group=self.process_group)
+        stride = p.parts.shape[1] * 2 * codebook_size                                  # records between two parts
+        _lib.check(lib.qpg_sliced_resolve(self._sliced_tables(p, q0, q1 - q0, part_q0, for_resolve=True), 2, p.world,
+                                          stride, q1 - q0, db.exact_offset, _lib.ptr(p.stats), sp), "qpg_sliced_resolve")
         return p.ta, p.tt
 
     def _launch_f64(self, p, sp):

@@ -49,7 +49,7 @@ class SlicedTable(C.Structure):
     _fields_ = [("packed", C.c_void_p), ("row_sqnorm", C.c_void_p), ("q", C.c_void_p), ("q_info", C.c_void_p),
                 ("ldq", C.c_int64), ("D", C.c_int32), ("pad", C.c_int32), ("sacc", C.c_void_p),
                 ("bin_start", C.c_void_p), ("row_info", C.c_void_p), ("order", C.c_void_p), ("bins", C.c_void_p),
-                ("table", C.c_void_p), ("ranks", C.c_void_p), ("qflags", C.c_void_p)]
+                ("bins_qstride", C.c_int64), ("table", C.c_void_p), ("ranks", C.c_void_p), ("qflags", C.c_void_p)]
 
 
 def dptr(t):

@@ -550,6 +550,7 @@ struct TableParams {         // device copy of qpg_sliced_table_t
   const RowInfo* row_info;
   const int32_t* order;
   qpg_bin_t* bins;
+  long long bins_qstride;   // records between two queries (512 when the table's records are contiguous)
   Pair* table;
   int32_t* ranks;
   int32_t* qflags;
@@ -679,7 +680,7 @@ __global__ void __launch_bounds__(256, 2)
         if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
       }
     }
-    if (lane == 0) T.bins[(size_t)qi_ * KB + c] = rec;
+    if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
     if (consume && c == KB - 1)                  // rows with a label outside [0, 512) belong to no bin
       for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
   }
@@ -736,7 +737,7 @@ __global__ void __launch_bounds__(KB)
   // merge: U* = min hi; candidates = parts with lo <= U*
   double U = 1e300;
   for (int p = 0; p < P; ++p) {
-    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + c];
+    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * T.bins_qstride + c];
     if (r.id >= 0) U = fmin(U, r.hi);
   }
   int ncand = 0;
@@ -744,7 +745,7 @@ __global__ void __launch_bounds__(KB)
   long long id = -1;
   bool exact = true;
   for (int p = 0; p < P; ++p) {
-    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + c];
+    const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * T.bins_qstride + c];
     if (r.id >= 0 && r.lo <= U) {
       if (ncand == 0) {
         lo = r.lo;
@@ -804,7 +805,7 @@ __global__ void __launch_bounds__(KB)
     double bd = 1e300;
     long long bid = -1;
     for (int p = 0; p < P; ++p) {
-      const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * KB + cc];
+      const qpg_bin_t r = parts[(size_t)p * part_stride + (size_t)qi_ * T.bins_qstride + cc];
       if (r.id >= 0 && r.lo <= Uc) {
         double d;
         if (r.flags & 1) d = r.lo;
@@ -985,6 +986,7 @@ static int fill_tables(const qpg_sliced_table_t* tabs, int n_tabs, bool for_bins
     o.row_info = reinterpret_cast<const RowInfo*>(t.row_info);
     o.order = t.order;
     o.bins = t.bins;
+    o.bins_qstride = t.bins_qstride > 0 ? t.bins_qstride : KB;
     o.table = reinterpret_cast<Pair*>(t.table);
     o.ranks = t.ranks;
     o.qflags = t.qflags;

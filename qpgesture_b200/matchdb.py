@@ -165,7 +165,7 @@ def column_exponents(rows: torch.Tensor):
     """Per-column power-of-two scaling for the fixed-point copy: None when the columns already share a
     magnitude (binary exponents of the column maxima within 2 of each other), else int8 [D] =
     floor(log2(max |x[:, k]|)) - median."""
-    colmax = rows.abs().amax(dim=0).to(torch.float64)
+    colmax = torch.maximum(rows.amax(dim=0), -rows.amin(dim=0)).to(torch.float64)      # no |rows| temporary
     ok = colmax > 0
     if not bool(ok.any()):
         return None

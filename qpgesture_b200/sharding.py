@@ -52,3 +52,21 @@ def plan_layout(db_bytes: int, world: int, min_shard_bytes: int = MIN_SHARD_BYTE
     while rs * 2 <= world and world % (rs * 2) == 0 and db_bytes // (rs * 2) >= min_shard_bytes:
         rs *= 2
     return rs, world // rs
+
+
+BIN_DTYPE = np.dtype([("lo", "<f8"), ("hi", "<f8"), ("id", "<i8"), ("n", "<i4"), ("flags", "<i4")])
+
+
+def merge_bin_records_host(parts_i64: np.ndarray):
+    """Host mirror of the merge step of qpg_sliced_resolve for tests.  parts int64 [P, ..., 4] (qpg_bin_t records of
+    P row shards) -> (candidates bool [P, ...]: shards whose interval reaches below the smallest interval end,
+    decided_id int64 [...]: the window id when exactly one shard remains (else -2), empty bins -1)."""
+    parts = np.ascontiguousarray(parts_i64).view(BIN_DTYPE).reshape(parts_i64.shape[:-1])
+    valid = parts["id"] >= 0
+    hi = np.where(valid, parts["hi"], np.inf)
+    U = hi.min(axis=0)
+    cand = valid & (parts["lo"] <= U[None])
+    n = cand.sum(axis=0)
+    first = cand.argmax(axis=0)
+    ids = np.take_along_axis(parts["id"], first[None], axis=0)[0]
+    return cand, np.where(n == 1, ids, np.where(n == 0, -1, -2))

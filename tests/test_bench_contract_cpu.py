@@ -23,7 +23,9 @@ def test_reference_arm_line():
     assert r["config"]["workload"] == "speaker10_24s" and r["config"]["windows"] == 13312
     assert r["e2e"] == {"value": r["value"], "unit": "s_audio/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     cb = r["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] == 1 and cb["value"] == r["value"] and "sample" in cb
+    # "reference" when the reference tree is present (this container), "port" on the GPU box
+    assert cb["kind"] in ("port", "reference") and cb["cores"] == 1 and cb["value"] == r["value"] and "sample" in cb
+    assert r["extrapolated"] is True and r["scale"] == 256.0 and cb["extrapolated"] is True
     assert 0 < r["value"] < 10
 
 

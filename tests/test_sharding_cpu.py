@@ -10,7 +10,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from oracle import matcher_np as om
-from qpgesture_b200.sharding import merge_tables_host, shard_sequences
+from qpgesture_b200.sharding import BIN_DTYPE, merge_bin_records_host, merge_tables_host, shard_sequences
 
 
 def test_shard_sequences_cover_and_order():
@@ -62,3 +62,56 @@ def test_gloo_two_rank_merge(tmp_path):
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     ok = np.load(out)
     assert ok.all()
+
+
+def _records_worker(rank, world, port, out):
+    """The sliced engine's exchange on CPU: per-bin interval records laid out [query][table][code], clips split
+    evenly -> ONE all_to_all_single gives every rank the records of its own clips from every shard."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(1)                        # same data on every rank
+    n_clips, steps, D, W = 4, 3, 16, 26 * 10
+    Q = n_clips * steps
+    rows = rng.standard_normal((W, D))
+    labels = rng.integers(0, 30, size=W)
+    q = rng.standard_normal((2, Q, D))                    # "audio" and "text" queries against the same rows
+    w0, w1 = rank * W // world, (rank + 1) * W // world
+    rec = np.zeros((Q, 2, 512), dtype=BIN_DTYPE)
+    rec["lo"], rec["hi"], rec["id"] = 1e3, 1e3, -1
+    for x in range(2):
+        for qi in range(Q):
+            d = om.cosine_rows(q[x, qi], rows[w0:w1])
+            bd, bw = om.min_by_code(d, labels[w0:w1])
+            ok = bw >= 0
+            rec["lo"][qi, x][ok] = bd[ok] - 1e-7            # an interval around the shard's best distance
+            rec["hi"][qi, x][ok] = bd[ok] + 1e-7
+            rec["id"][qi, x][ok] = bw[ok] + w0
+    send = torch.from_numpy(rec.view(np.int64).reshape(Q, 2, 512, 4).copy())
+    per = Q // world
+    recv = torch.empty((world, per, 2, 512, 4), dtype=torch.int64)
+    dist.all_to_all_single(recv, send)                      # chunk r of `send` = queries of rank r's clips
+    cand, decided = merge_bin_records_host(recv.numpy())
+    mine = slice(rank * per, (rank + 1) * per)
+    ok = True
+    for x in range(2):
+        for i, qi in enumerate(range(mine.start, mine.stop)):
+            d = om.cosine_rows(q[x, qi], rows)
+            bd, bw = om.min_by_code(d, labels)
+            dec = decided[i, x]
+            settled = dec != -2                             # -2: several shards within 2e-7, float64 decides on the GPU
+            ok &= bool(np.array_equal(dec[settled], bw[settled]))
+            ok &= bool((dec == -2).sum() <= 2)
+    res = torch.tensor([int(ok)])
+    dist.all_reduce(res, op=dist.ReduceOp.MIN)
+    if rank == 0:
+        np.save(out, np.array([int(res.item())]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_two_rank_record_exchange(tmp_path):
+    out = str(tmp_path / "ok2.npy")
+    port = 31500 + (os.getpid() % 2000)
+    mp.spawn(_records_worker, args=(2, port, out), nprocs=2, join=True)
+    assert np.load(out).all()

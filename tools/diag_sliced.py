@@ -36,10 +36,10 @@ segs[0].db_slices, segs[0].q_slices, segs[0].sacc, segs[0].n_kblocks = A.slices.
 segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
 lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, _lib.stream_ptr())
 torch.cuda.synchronize()
-bins = p.bins.cpu().numpy()            # [2, Q, 512, 4] int64
+bins = p.bins.cpu().numpy()            # [Q, 2, 512, 4] int64
 out = {"stats": p.stats.cpu().tolist()}
 for x, name in enumerate(("audio", "text")):
-    b = bins[x]
+    b = bins[:, x]
     lo = b[..., 0].view(np.float64); hi = b[..., 1].view(np.float64); ids = b[..., 2]
     nf = b[..., 3]
     ncand = (nf & 0xffffffff).astype(np.int64); flags = (nf >> 32).astype(np.int64)
