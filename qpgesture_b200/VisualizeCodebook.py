@@ -83,10 +83,19 @@ def cal_distance(args, model_path, save_path, prefix, normalize=True, model=None
     return code, poses, np.mean(poses, axis=1)
 
 
-def visualizeCodeAndWrite(config, code_path=None, prefix="knn_pred_wavvq", save_path=None, model_path=None):
-    """Inference half of VisualizeCodebook.py:333-370 (code file -> poses); stops before the BVH step."""
-    code_source = np.load(code_path)["knn_pred"]
-    return visualize_code(config, model_path, save_path, prefix, code_source)
+def visualizeCodeAndWrite(code_path=None, save_path="./Speech2GestureMatching/output/", prefix=None,
+                          pipeline_path="../data/data_pipe_60_rotation.sav", generateGT=True, code_source=None, vis=True,
+                          *, config=None, model_path=None, model=None):
+    """Inference half of VisualizeCodebook.py:333-370 (code file -> poses) with the reference's positional
+    arguments; the files go to os.path.join(save_path, prefix) like the reference's (:342), which is where its BVH
+    step (not built: needs the unshipped data_pipe_60_rotation.sav) looks for them.  `config` (keyword, the
+    reference reads a module global) carries VQVAE / data_mean / data_std / VQVAE_model_path."""
+    assert config is not None, "pass config= (the reference reads a module-level global)"
+    if code_source is None:
+        code_source = np.load(code_path)["knn_pred"]                     # :357
+    model_path = model_path or getattr(config, "VQVAE_model_path", None)
+    save_path = os.path.join(save_path, prefix)                          # :342
+    return visualize_code(config, model_path, save_path, prefix, code_source, model=model)
 
 
 def main(argv=None):
@@ -103,8 +112,8 @@ def main(argv=None):
         model = load_model(config, a.VQVAE_model_path, dev)
         return cal_distance(config, a.VQVAE_model_path, a.save_path, a.prefix, model=model)
     model = load_model(config, a.VQVAE_model_path, dev)
-    code_source = np.load(a.code_path)["knn_pred"]
-    return visualize_code(config, a.VQVAE_model_path, a.save_path, a.prefix, code_source, model=model)
+    return visualizeCodeAndWrite(code_path=a.code_path, prefix=a.prefix, generateGT=False, save_path=a.save_path,
+                                 config=config, model=model)            # :393
 
 
 

@@ -314,11 +314,8 @@ extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in
     }
   }
   const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
-  static bool attr_set = false;
-  if (!attr_set) {
-    QPG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
-  }
+  // the attribute is per device: set it on every launch (a process may use several GPUs)
+  QPG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles_b = (d->B + p.Bbox - 1) / p.Bbox;
   dim3 grid((unsigned)(tiles_b * p.tiles_t), (unsigned)(d->N_pad / d->BN));
   conv_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(map_a, map_b, p, bias, residual, out, out_relu);

@@ -141,11 +141,8 @@ extern "C" int qpg_vq_argmin_f32(const float* x, const float* codebook, int64_t 
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(idx_out);
   vq_key_init_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(keys, M);
   QPG_LAUNCH_CHECK();
-  static bool attr_set = false;
-  if (!attr_set) {
-    QPG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  // the attribute is per device: set it on every launch (a process may use several GPUs)
+  QPG_CUDA(cudaFuncSetAttribute(vq_argmin_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
   dim3 grid((unsigned)((M + TM - 1) / TM), (unsigned)((K + THREADS - 1) / THREADS));
   vq_argmin_kernel<<<grid, THREADS, smem, st>>>(x, codebook, M, D, K, keys);
   QPG_LAUNCH_CHECK();

@@ -330,6 +330,9 @@ class BottleneckBlock:
         """int64 [...] -> float32 [..., emb]  (F.embedding, bottleneck.py:128-130)."""
         lib = _lib.load()
         flat = x_l.reshape(-1).contiguous()
+        if flat.numel() and (int(flat.min()) < 0 or int(flat.max()) >= self.k_bins):
+            # F.embedding raises on an out-of-range index; e.g. the -1 rows a failed match leaves in knn_pred
+            raise IndexError(f"code index out of range [0, {self.k_bins}): min {int(flat.min())}, max {int(flat.max())}")
         out = torch.empty((flat.shape[0], self.emb_width), dtype=torch.float32, device=flat.device)
         _lib.check(lib.qpg_vq_dequantise_f32(_lib.ptr(flat), _lib.ptr(self.k), flat.shape[0], self.emb_width,
                                              self.k_bins, _lib.ptr(out), _lib.stream_ptr()), "qpg_vq_dequantise_f32")
