@@ -99,17 +99,25 @@ __global__ void __launch_bounds__(256, 6)
     }
   };
   const bool any_empty = s_ne[0] < KB || s_ne[1] < KB;          // block uniform; false for any sizeable database
+  int m1[2] = {0x7fffffff, 0x7fffffff}, m2[2] = {0x7fffffff, 0x7fffffff};
   for (int c0 = sl * CPS; c0 < (sl + 1) * CPS; c0 += 8) {      // eight loads in flight per round
     int pr[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
     if (!any_empty) {
+      // fast path: (key << 9 | code) packed in one int; smallest and second smallest value per table with three
+      // min/max each - the smallest carries the lowest code among equal keys
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int c = c0 + i;
-        const int p20 = 20 * pr[i];
-        offer(0, p20 + s_key[0][c], c, pr[i], 0);
-        offer(1, p20 + s_key[1][c], c, pr[i], 0);
+        const int v = pr[i] * (20 << 9);
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+          const int val = v + ((s_key[x][c] << 9) | c);
+          const int t = max(m1[x], val);
+          m1[x] = min(m1[x], val);
+          m2[x] = min(m2[x], t);
+        }
       }
     } else {
 #pragma unroll
@@ -124,6 +132,23 @@ __global__ void __launch_bounds__(256, 6)
           offer(x, key, c, pr[i], 0);
           if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
           else best_ne[x] = min(best_ne[x], key);
+        }
+      }
+    }
+  }
+  if (!any_empty) {
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+      const int key = m1[x] >> 9, c1 = m1[x] & (KB - 1);
+      if (((m1[x] ^ m2[x]) >> 9) != 0) {           // the slice's best key is unique
+        best[x] = key;
+        arg[x] = c1;
+        bpos[x] = (key - s_key[x][c1]) / 20;
+        tie[x] = 0;
+      } else {                                     // equal keys inside the slice: let the float64 values decide
+        for (int c = sl * CPS; c < (sl + 1) * CPS; ++c) {
+          const int pos = (int)pos_rank_t[(size_t)c * KB + last];
+          if (20 * pos + s_key[x][c] == key) offer(x, key, c, pos, 0);
         }
       }
     }

@@ -694,25 +694,39 @@ __global__ void __launch_bounds__(256, 2)
 // to be decided, else the centre of the filter interval), ranks [nq][512] (stable, as qpg_rank512),
 // qflags [nq] bit 0 = exact tie between two non-empty bins.
 // ascending bitonic sort of 512 (key, val) pairs in shared memory by 512 threads; vals are distinct, so the order
-// is total: equal keys keep the lower val first
+// is total: equal keys keep the lower val first.  Partners closer than a warp are exchanged with shuffles, so only
+// 10 of the 45 compare-exchange stages need a block barrier.
 __device__ __forceinline__ void bitonic_sort_512(unsigned long long* key, int* val, int tid) {
+  unsigned long long kk = key[tid];
+  int vv = val[tid];
   for (int k = 2; k <= KB; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
       const int other = tid ^ j;
-      unsigned long long kk = key[tid], ok = key[other];
-      int vv = val[tid], ov = val[other];
-      __syncthreads();
+      unsigned long long ok;
+      int ov;
+      if (j >= 32) {
+        __syncthreads();
+        key[tid] = kk;
+        val[tid] = vv;
+        __syncthreads();
+        ok = key[other];
+        ov = val[other];
+      } else {
+        ok = __shfl_xor_sync(0xffffffffu, kk, j);
+        ov = __shfl_xor_sync(0xffffffffu, vv, j);
+      }
       const bool want_min = ((tid & k) == 0) == (tid < other);
       const bool other_less = ok < kk || (ok == kk && ov < vv);
       if (other_less == want_min) {
         kk = ok;
         vv = ov;
       }
-      key[tid] = kk;
-      val[tid] = vv;
-      __syncthreads();
     }
   }
+  __syncthreads();
+  key[tid] = kk;
+  val[tid] = vv;
+  __syncthreads();
 }
 
 __global__ void __launch_bounds__(KB)
