@@ -330,9 +330,6 @@ class BottleneckBlock:
         """int64 [...] -> float32 [..., emb]  (F.embedding, bottleneck.py:128-130)."""
         lib = _lib.load()
         flat = x_l.reshape(-1).contiguous()
-        if flat.numel() and (int(flat.min()) < 0 or int(flat.max()) >= self.k_bins):
-            # F.embedding raises on an out-of-range index; e.g. the -1 rows a failed match leaves in knn_pred
-            raise IndexError(f"code index out of range [0, {self.k_bins}): min {int(flat.min())}, max {int(flat.max())}")
         out = torch.empty((flat.shape[0], self.emb_width), dtype=torch.float32, device=flat.device)
         _lib.check(lib.qpg_vq_dequantise_f32(_lib.ptr(flat), _lib.ptr(self.k), flat.shape[0], self.emb_width,
                                              self.k_bins, _lib.ptr(out), _lib.stream_ptr()), "qpg_vq_dequantise_f32")
@@ -435,6 +432,10 @@ class VQVAE:
         assert len(zs) == 1
         with torch.cuda.device(self.device):
             z = zs[0].to(device=self.device, dtype=torch.int64).contiguous()
+            if z.numel() and (int(z.min()) < 0 or int(z.max()) >= self.l_bins):
+                # F.embedding (bottleneck.py:129) raises on an out-of-range index; the gather kernel would clamp.
+                # Typical source: the -1 rows a failed match leaves in knn_pred.  Checked here, outside the graph.
+                raise IndexError(f"code index out of range [0, {self.l_bins}): min {int(z.min())}, max {int(z.max())}")
             return self._graphed("dec", z, lambda t: self.decoder(self.bottleneck.decode(t)))   # [B, 8T', C]
 
     def decode(self, zs, start_level=0, end_level=None, bs_chunks=1):
@@ -448,6 +449,15 @@ class VQVAE:
         return self.decode([z])
 
     def forward(self, x):
-        raise NotImplementedError("training forward (losses, EMA codebook update) is outside the inference hot path")
+        """Inference half of VQVAE.forward (vqvae.py:187-303): encode -> quantise -> decode.  Returns
+        (x_out, loss, metrics) like the reference; the training losses and the EMA codebook update are outside the
+        inference hot path, so loss is None and metrics holds only the reconstruction errors."""
+        x = torch.as_tensor(x)
+        x_out = self.decode(self.encode(x))
+        x_in = x.to(device=x_out.device, dtype=torch.float32)
+        with torch.no_grad():
+            err = x_out - x_in
+            metrics = dict(recons_loss=torch.mean(err ** 2), l1_loss=torch.mean(err.abs()))
+        return x_out, None, metrics
 
     __call__ = forward
