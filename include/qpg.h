@@ -306,6 +306,11 @@ int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_
  */
 int qpg_vq_argmin_f32(const float* x, const float* codebook, int64_t M, int D, int K, int64_t* idx_out,
                       float* min_out, void* stream);
+/* Same result, tensor-core filter + exact re-evaluation: X * C^T on tcgen05 (TF32, qpg_conv1d_taps_tf32) into
+ * `scratch` (float32 [M*K + K]), then only the codes whose distance could be minimal under the TF32 error bound are
+ * evaluated with the arithmetic above (typically 2-6 of 512).  Needs D % 4 == 0, K % 16 == 0. */
+int qpg_vq_argmin_fast(const float* x, const float* codebook, int64_t M, int D, int K, float* scratch,
+                       int64_t* idx_out, float* min_out, void* stream);
 /* BottleneckBlock.dequantise (bottleneck.py:128-130): out[m,:] = codebook[idx[m],:] */
 int qpg_vq_dequantise_f32(const int64_t* idx, const float* codebook, int64_t M, int D, int K, float* out,
                           void* stream);
@@ -358,6 +363,12 @@ typedef struct {
 } qpg_conv_tc_desc_t;
 int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* desc, const float* in, const float* w, const float* bias,
                          const float* residual, float* out, float* out_relu, void* stream);
+/* Same tap GEMM with float32-accurate products on the TF32 tensor cores (3xTF32): x*w ~ x_hi*w_hi + x_lo*w_hi +
+ * x_hi*w_lo.  w_hi = w with the low 13 mantissa bits cleared, w_lo = (w - w_hi) with its low 13 bits cleared (both
+ * in the layout of `w` above); the activations are split inside the kernel.  BN <= 128.  Products are accurate to
+ * ~2^-21 relative (float32 FFMA: 2^-24), which is what the index-parity mode of the VQ-VAE needs. */
+int qpg_conv1d_taps_3xtf32(const qpg_conv_tc_desc_t* desc, const float* in, const float* w_hi, const float* w_lo,
+                           const float* bias, const float* residual, float* out, float* out_relu, void* stream);
 
 #ifdef __cplusplus
 }

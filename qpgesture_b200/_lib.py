@@ -95,9 +95,11 @@ SIGNATURES = {
     "qpg_match_tail_segments": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _P, _INT, _INT, _INT, _INT, _P,
                                        _P, _P, _P, _P, _P]),
     "qpg_vq_argmin_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P]),
+    "qpg_vq_argmin_fast": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P, _P, _P]),
     "qpg_vq_dequantise_f32": (_INT, [_P, _P, _I64, _INT, _INT, _P, _P]),
     "qpg_conv1d_taps_f32": (_INT, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "qpg_conv1d_taps_tf32": (_INT, [C.POINTER(ConvTcDesc), _P, _P, _P, _P, _P, _P, _P]),
+    "qpg_conv1d_taps_3xtf32": (_INT, [C.POINTER(ConvTcDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
 }
 
 

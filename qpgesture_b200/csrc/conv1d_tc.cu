@@ -94,6 +94,60 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ===== epilogue: TMEM -> registers -> global (warps 4-7 of either kernel) =====
+__device__ __forceinline__ void conv_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* accum_full, int warp,
+                                              int lane, int b0, int t0, int n0, const float* __restrict__ bias,
+                                              const float* __restrict__ residual, float* __restrict__ out,
+                                              float* __restrict__ out_relu) {
+  const int q = warp & 3;                       // TMEM lane quarter this warp may access
+  const int r = q * 32 + lane;                  // row of the tile
+  const int b_local = r / p.Tbox, t_local = r - b_local * p.Tbox;
+  const bool row_ok = r < p.Bbox * p.Tbox && (b0 + b_local) < p.B && (t0 + t_local) < p.n_out;
+  const size_t row_base = ((size_t)(b0 + b_local) * p.out_rows_per_item + (t0 + t_local)) * (size_t)p.out_ld +
+                          p.out_chan_off;
+  const bool vec = (p.out_ld & 3) == 0 && (p.out_chan_off & 3) == 0;
+  mbar_wait(accum_full, 0);
+  tc_fence_after();
+  for (int cc = 0; cc < p.BN; cc += 32) {
+    uint32_t v[32];
+    __syncwarp();
+    tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
+    if (!row_ok) continue;
+    const int ncol = n0 + cc;                   // first output channel of this chunk
+    if (vec && ncol + 32 <= p.C_out) {
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                               __uint_as_float(v[j + 3]));
+        if (bias) {
+          const float4 bb = *reinterpret_cast<const float4*>(bias + ncol + j);
+          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+        }
+        if (residual) {
+          const float4 rr = *reinterpret_cast<const float4*>(residual + row_base + ncol + j);
+          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
+        }
+        if (out) *reinterpret_cast<float4*>(out + row_base + ncol + j) = o;
+        if (out_relu)
+          *reinterpret_cast<float4*>(out_relu + row_base + ncol + j) =
+              make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int n = ncol + j;
+        if (n < p.C_out) {
+          float o = __uint_as_float(v[j]);
+          if (bias) o += bias[n];
+          if (residual) o += residual[row_base + n];
+          if (out) out[row_base + n] = o;
+          if (out_relu) out_relu[row_base + n] = fmaxf(o, 0.f);
+        }
+      }
+    }
+  }
+}
+
 // ---- kernel -----------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p,
@@ -174,54 +228,137 @@ __global__ void __launch_bounds__(256, 1)
       tc_commit(accum_full);       // accumulator complete
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int q = warp & 3;                       // TMEM lane quarter this warp may access
-    const int r = q * 32 + lane;                  // row of the tile
-    const int b_local = r / p.Tbox, t_local = r - b_local * p.Tbox;
-    const bool row_ok = r < p.Bbox * p.Tbox && (b0 + b_local) < p.B && (t0 + t_local) < p.n_out;
-    const size_t row_base = ((size_t)(b0 + b_local) * p.out_rows_per_item + (t0 + t_local)) * (size_t)p.out_ld +
-                            p.out_chan_off;
-    const bool vec = (p.out_ld & 3) == 0 && (p.out_chan_off & 3) == 0;
-    mbar_wait(accum_full, 0);
+    conv_epilogue(p, tmem_base, accum_full, warp, lane, b0, t0, n0, bias, residual, out, out_relu);
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
     tc_fence_after();
-    for (int cc = 0; cc < p.BN; cc += 32) {
-      uint32_t v[32];
-      __syncwarp();
-      tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-      if (!row_ok) continue;
-      const int ncol = n0 + cc;                   // first output channel of this chunk
-      if (vec && ncol + 32 <= p.C_out) {
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (bias) {
-            const float4 bb = *reinterpret_cast<const float4*>(bias + ncol + j);
-            o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
-          }
-          if (residual) {
-            const float4 rr = *reinterpret_cast<const float4*>(residual + row_base + ncol + j);
-            o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-          }
-          if (out) *reinterpret_cast<float4*>(out + row_base + ncol + j) = o;
-          if (out_relu)
-            *reinterpret_cast<float4*>(out_relu + row_base + ncol + j) =
-                make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          const int n = ncol + j;
-          if (n < p.C_out) {
-            float o = __uint_as_float(v[j]);
-            if (bias) o += bias[n];
-            if (residual) o += residual[row_base + n];
-            if (out) out[row_base + n] = o;
-            if (out_relu) out_relu[row_base + n] = fmaxf(o, 0.f);
-          }
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
+  }
+}
+
+// ---- 3xTF32: float32-accurate products on the TF32 tensor cores ------------------------------------------
+// x*w ~ x_hi*w_hi + x_lo*w_hi + x_hi*w_lo with x_hi = x truncated to TF32 (11 significant bits) and x_lo = x - x_hi
+// (exact in float32; its own truncation to TF32 and the dropped x_lo*w_lo are both ~2^-22 relative).  The weights
+// arrive pre-split from the host (w_hi, w_lo: two tensor maps); the activation tile is split IN SHARED MEMORY by
+// four extra warps (8-11) between the TMA arrival and the MMAs: A is masked in place to its TF32 part and
+// A - A_hi goes to a second buffer, so activations stay single float32 arrays in HBM and the epilogue is
+// unchanged.  Three MMAs per k-step into the same accumulator.  Stage = A, A_lo, B_hi, B_lo (16 KiB each, BN <= 128),
+// three stages.
+constexpr int SPLIT_STAGES = 3;
+constexpr int SPLIT_BN = 128;
+constexpr int SPLIT_STAGE_BYTES = 4 * A_BYTES;
+
+__global__ void __launch_bounds__(384, 1)
+    conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
+                    const __grid_constant__ CUtensorMap map_b_lo, TcParams p, const float* __restrict__ bias,
+                    const float* __restrict__ residual, float* __restrict__ out, float* __restrict__ out_relu) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + SPLIT_STAGES * SPLIT_STAGE_BYTES);
+  uint64_t* empty = full + SPLIT_STAGES;
+  uint64_t* split = empty + SPLIT_STAGES;
+  uint64_t* accum_full = split + SPLIT_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
+  const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
+  const int b0 = tb * p.Bbox, t0 = tt * p.Tbox;
+  const int n_iter = p.n_taps * p.kblocks;
+  const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b_lo) : "memory");
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < SPLIT_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&split[s], 4);              // one arrive per splitter warp
+    }
+    mbar_init(accum_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {                                       // ===== TMA producer =====
+      const uint32_t a_bytes = (uint32_t)p.Bbox * p.Tbox * 128u, b_bytes = (uint32_t)p.BN * 128u;
+      int it = 0;
+      for (int tap = 0; tap < p.n_taps; ++tap) {
+        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+          const int s = it % SPLIT_STAGES;
+          if (it >= SPLIT_STAGES) mbar_wait(&empty[s], ((it / SPLIT_STAGES) - 1) & 1);
+          unsigned char* st = smem + s * SPLIT_STAGE_BYTES;
+          mbar_arrive_expect_tx(&full[s], a_bytes + 2 * b_bytes);
+          tma_load_3d(st, &map_a, &full[s], p.chan_off[tap] + kb * BK, t0 + p.row_off[tap], b0);
+          tma_load_2d(st + 2 * A_BYTES, &map_b, &full[s], kb * BK, tap * p.N_pad + n0);
+          tma_load_2d(st + 3 * A_BYTES, &map_b_lo, &full[s], kb * BK, tap * p.N_pad + n0);
         }
       }
     }
+  } else if (warp == 1) {
+    if (lane == 0) {                                       // ===== MMA issuer =====
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int it = 0; it < n_iter; ++it) {
+        const int s = it % SPLIT_STAGES;
+        mbar_wait(&split[s], (it / SPLIT_STAGES) & 1);      // TMA landed AND the activation tile is split
+        tc_fence_after();
+        const uint32_t st = smem_u32(smem + s * SPLIT_STAGE_BYTES);
+        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + A_BYTES);
+        const uint64_t b_hi = umma_desc_sw128(st + 2 * A_BYTES), b_lo = umma_desc_sw128(st + 3 * A_BYTES);
+#pragma unroll
+        for (int k = 0; k < BK / UMMA_K; ++k) {
+          tc_mma_tf32(tmem_base, a_lo + 2u * k, b_hi + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);   // small terms first
+          tc_mma_tf32(tmem_base, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+          tc_mma_tf32(tmem_base, a_hi + 2u * k, b_hi + 2u * k, idesc, 1u);
+        }
+        tc_commit(&empty[s]);
+      }
+      tc_commit(accum_full);
+    }
+  } else if (warp >= 8) {
+    // ===== splitter: A -> (A_hi in place, A_lo) for the whole 16 KiB tile; elementwise, so the swizzle is irrelevant
+    const int t = threadIdx.x - 256;                       // 0..127
+    for (int it = 0; it < n_iter; ++it) {
+      const int s = it % SPLIT_STAGES;
+      mbar_wait(&full[s], (it / SPLIT_STAGES) & 1);
+      float4* a = reinterpret_cast<float4*>(smem + s * SPLIT_STAGE_BYTES);
+      float4* lo = reinterpret_cast<float4*>(smem + s * SPLIT_STAGE_BYTES + A_BYTES);
+#pragma unroll
+      for (int j = 0; j < A_BYTES / 16 / 128; ++j) {
+        const int i = j * 128 + t;
+        const float4 v = a[i];
+        float4 h;
+        h.x = __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+        h.y = __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+        h.z = __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+        h.w = __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+        a[i] = h;
+        lo[i] = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
+      }
+      fence_proxy_async();                                 // generic-proxy writes -> visible to the tensor core reads
+      __syncwarp();
+      if (lane == 0) {
+        asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&split[s])) : "memory");
+      }
+    }
+  } else if (warp >= 4) {
+    conv_epilogue(p, tmem_base, accum_full, warp, lane, b0, t0, n0, bias, residual, out, out_relu);
   }
 
   tc_fence_before();
@@ -254,18 +391,21 @@ EncodeTiledFn get_encode_fn() {
 
 using namespace qpg;
 
-extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in, const float* w, const float* bias,
-                                    const float* residual, float* out, float* out_relu, void* stream) {
+static int conv_tc_launch(const qpg_conv_tc_desc_t* d, const float* in, const float* w, const float* w_lo,
+                          const float* bias, const float* residual, float* out, float* out_relu, void* stream) {
+  const bool split = w_lo != nullptr;
   QPG_CHECK_ARG(d != nullptr, "null descriptor");
   QPG_CHECK_ARG(d->B >= 0 && d->T_view > 0 && d->C_view > 0 && d->C_in > 0 && d->C_out > 0, "bad shape");
   QPG_CHECK_ARG(d->n_taps >= 1 && d->n_taps <= 4 && d->n_out >= 0, "n_taps in 1..4");
   QPG_CHECK_ARG((d->C_view & 3) == 0 && (d->K_pad & 3) == 0 && d->K_pad >= d->C_in,
                 "C_view and K_pad must be multiples of 4 floats (16-byte TMA strides)");
-  QPG_CHECK_ARG(d->BN >= 16 && d->BN <= MAX_BN && (d->BN & 15) == 0 && d->N_pad % d->BN == 0 && d->N_pad >= d->C_out,
-                "BN multiple of 16 <= 256, N_pad multiple of BN");
+  QPG_CHECK_ARG(d->BN >= 16 && d->BN <= (split ? SPLIT_BN : MAX_BN) && (d->BN & 15) == 0 && d->N_pad % d->BN == 0 &&
+                    d->N_pad >= d->C_out,
+                "BN multiple of 16 <= 256 (<= 128 for 3xTF32), N_pad multiple of BN");
   if (d->B == 0 || d->n_out == 0) return QPG_OK;
   QPG_CHECK_ARG(in && w && (out || out_relu), "null pointer");
-  QPG_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w)) & 15) == 0, "16-byte alignment");
+  QPG_CHECK_ARG(((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(w) | reinterpret_cast<uintptr_t>(w_lo)) & 15) == 0,
+                "16-byte alignment");
   EncodeTiledFn encode = get_encode_fn();
   if (!encode) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -286,7 +426,7 @@ extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in
   p.kblocks = (d->C_in + BK - 1) / BK;
   p.out_rows_per_item = d->out_rows_per_item; p.out_ld = d->out_ld; p.out_chan_off = d->out_chan_offset;
 
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_b_lo;
   {
     cuuint64_t dims[3] = {(cuuint64_t)d->C_view, (cuuint64_t)d->T_view, (cuuint64_t)d->B};
     cuuint64_t strides[2] = {(cuuint64_t)d->C_view * 4, (cuuint64_t)d->C_view * 4 * (cuuint64_t)d->T_view};
@@ -300,12 +440,13 @@ extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in
       return QPG_E_CUDA;
     }
   }
-  {
+  for (int which = 0; which < (split ? 2 : 1); ++which) {
     cuuint64_t dims[2] = {(cuuint64_t)d->K_pad, (cuuint64_t)d->n_taps * (cuuint64_t)d->N_pad};
     cuuint64_t strides[1] = {(cuuint64_t)d->K_pad * 4};
     cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)d->BN};
     cuuint32_t estr[2] = {1, 1};
-    CUresult rc = encode(&map_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(w), dims, strides, box, estr,
+    CUresult rc = encode(which == 0 ? &map_b : &map_b_lo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                         const_cast<float*>(which == 0 ? w : w_lo), dims, strides, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (rc != CUDA_SUCCESS) {
@@ -313,12 +454,33 @@ extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in
       return QPG_E_CUDA;
     }
   }
-  const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
-  // the attribute is per device: set it on every launch (a process may use several GPUs)
-  QPG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const int tiles_b = (d->B + p.Bbox - 1) / p.Bbox;
   dim3 grid((unsigned)(tiles_b * p.tiles_t), (unsigned)(d->N_pad / d->BN));
-  conv_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(map_a, map_b, p, bias, residual, out, out_relu);
+  // the shared-memory attribute is per device: set it on every launch (a process may use several GPUs)
+  if (split) {
+    const size_t smem = (size_t)SPLIT_STAGES * SPLIT_STAGE_BYTES + (3 * SPLIT_STAGES + 1) * sizeof(uint64_t) + 16;
+    QPG_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc3_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(map_a, map_b, map_b_lo, p, bias, residual, out, out_relu);
+  } else {
+    const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+    QPG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(map_a, map_b, p, bias, residual, out, out_relu);
+  }
   QPG_LAUNCH_CHECK();
   return QPG_OK;
+}
+
+extern "C" int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* d, const float* in, const float* w, const float* bias,
+                                    const float* residual, float* out, float* out_relu, void* stream) {
+  return conv_tc_launch(d, in, w, nullptr, bias, residual, out, out_relu, stream);
+}
+
+extern "C" int qpg_conv1d_taps_3xtf32(const qpg_conv_tc_desc_t* d, const float* in, const float* w_hi, const float* w_lo,
+                                      const float* bias, const float* residual, float* out, float* out_relu,
+                                      void* stream) {
+  if (w_lo == nullptr) {
+    set_error("bad argument: w_lo is null");
+    return QPG_E_BADARG;
+  }
+  return conv_tc_launch(d, in, w_hi, w_lo, bias, residual, out, out_relu, stream);
 }

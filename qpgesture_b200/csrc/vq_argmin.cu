@@ -113,6 +113,81 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
+// ---- fast path: tensor-core filter + exact re-evaluation of the near-minimal codes --------------------------
+// G = X * C^T comes from the tcgen05 TF32 tap-GEMM (conv1d_tc.cu, one tap).  TF32 truncates both operands to 11
+// significant bits, so |G~ - G| <= ~2^-9 * sum|x_i c_i| <= 2^-9 |x||c|; with the margin below every code whose
+// exact distance could be the minimum is re-evaluated with the SAME arithmetic as vq_argmin_kernel (float64
+// inner product rounded once, then the reference's two float32 roundings) and the lexicographic (distance,
+// index) minimum over those is taken - the result is the exact kernel's, at a fraction of its cost (typically
+// 2-6 of the 512 codes per latent survive the filter).  One warp per latent.
+__global__ void vq_code_norms_kernel(const float* __restrict__ cb, int D, int K, float* __restrict__ kn_out) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  const float* row = cb + (size_t)k * D;
+  double kn = 0.0;                                                  // same ascending order as vq_argmin_kernel
+  for (int d = 0; d < D; ++d) kn = fma((double)row[d], (double)row[d], kn);
+  kn_out[k] = (float)kn;
+}
+
+__global__ void __launch_bounds__(256)
+    vq_select_kernel(const float* __restrict__ x, const float* __restrict__ cb, const float* __restrict__ G,
+                     const float* __restrict__ kn_in, int64_t M, int D, int K, int64_t* __restrict__ idx_out,
+                     float* __restrict__ min_out) {
+  extern __shared__ float s_kn[];                                   // [K] |c_k|^2 (float64 accumulated, rounded)
+  for (int k = threadIdx.x; k < K; k += blockDim.x) s_kn[k] = kn_in[k];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t m = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+  if (m >= M) return;
+  const float* xr = x + (size_t)m * D;
+  double xs = 0.0;
+  for (int d = lane; d < D; d += 32) xs = fma((double)xr[d], (double)xr[d], xs);
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) xs += __shfl_xor_sync(0xffffffffu, xs, o);
+  // vq_argmin_kernel sums the squares of a latent in the same lane-strided order, so xn is bit-identical
+  const float xn = (float)xs;
+  const float xnorm = sqrtf(xn);
+  // approximate distances (without the common |x|^2) and the acceptance bound per code
+  float best = 3.0e38f;
+  for (int k = lane; k < K; k += 32) {
+    const float g = G[(size_t)m * K + k];
+    const float kn = s_kn[k];
+    const float hi = (kn - 2.0f * g) + 0.0079f * xnorm * sqrtf(kn) + 2e-6f * (xn + kn);     // upper bound of the exact value
+    best = fminf(best, hi);
+  }
+#pragma unroll
+  for (int o = 16; o >= 1; o >>= 1) best = fminf(best, __shfl_xor_sync(0xffffffffu, best, o));
+  unsigned long long key = ~0ull;
+  for (int k0 = 0; k0 < K; k0 += 32) {
+    const int k = k0 + lane;
+    bool cand = false;
+    if (k < K) {
+      const float g = G[(size_t)m * K + k];
+      const float kn = s_kn[k];
+      const float lo = (kn - 2.0f * g) - 0.0079f * xnorm * sqrtf(kn) - 2e-6f * (xn + kn);   // lower bound
+      cand = lo <= best;
+    }
+    unsigned mask = __ballot_sync(0xffffffffu, cand);
+    while (mask) {
+      const int src = __ffs(mask) - 1;
+      mask &= mask - 1;
+      const int kc = k0 + src;
+      const float* row = cb + (size_t)kc * D;
+      double acc = 0.0;
+      for (int d = lane; d < D; d += 32) acc = fma((double)xr[d], (double)row[d], acc);
+#pragma unroll
+      for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      const float dist = __fadd_rn(__fsub_rn(xn, __fmul_rn(2.0f, (float)acc)), s_kn[kc]);
+      const unsigned long long kk = ((unsigned long long)ordered_u32(dist) << 32) | (unsigned long long)kc;
+      key = kk < key ? kk : key;
+    }
+  }
+  if (lane == 0) {
+    idx_out[m] = (int64_t)(key & 0xffffffffull);
+    if (min_out) min_out[m] = unordered_f32((uint32_t)(key >> 32));
+  }
+}
+
 __global__ void dequantise_kernel(const int64_t* __restrict__ idx, const float* __restrict__ cb, int64_t M, int D,
                                   int K, float* __restrict__ out) {
   const int64_t m = blockIdx.x;
@@ -157,6 +232,41 @@ extern "C" int qpg_vq_dequantise_f32(const int64_t* idx, const float* codebook, 
   if (M == 0) return QPG_OK;
   QPG_CHECK_ARG(idx && codebook && out, "null pointer");
   dequantise_kernel<<<(unsigned)M, 128, 0, (cudaStream_t)stream>>>(idx, codebook, M, D, K, out);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_vq_argmin_fast(const float* x, const float* codebook, int64_t M, int D, int K, float* scratch,
+                                  int64_t* idx_out, float* min_out, void* stream) {
+  QPG_CHECK_ARG(M >= 0 && D > 0 && K > 0, "M >= 0, D > 0, K > 0");
+  if (M == 0) return QPG_OK;
+  QPG_CHECK_ARG(x && codebook && idx_out && scratch, "null pointer");
+  QPG_CHECK_ARG(D % 4 == 0 && K % 16 == 0 && K <= 12288 && M < (1ll << 31), "needs D % 4 == 0, K % 16 == 0");
+  // G[M, K] = X * C^T on the tensor cores: the latents as a one-item sequence of M frames, the codebook as the
+  // (K-major) weights of a single tap
+  qpg_conv_tc_desc_t d;
+  d.B = 1;
+  d.T_view = (int)M;
+  d.C_view = D;
+  d.n_out = (int)M;
+  d.C_in = D;
+  d.C_out = K;
+  d.K_pad = D;
+  d.BN = K % 256 == 0 ? 256 : (K % 128 == 0 ? 128 : (K % 64 == 0 ? 64 : 16));
+  d.N_pad = K;
+  d.n_taps = 1;
+  for (int i = 0; i < 4; ++i) d.row_offset[i] = d.chan_offset[i] = 0;
+  d.out_rows_per_item = (int)M;
+  d.out_ld = K;
+  d.out_chan_offset = 0;
+  const int rc = qpg_conv1d_taps_tf32(&d, x, codebook, nullptr, nullptr, scratch, nullptr, stream);
+  if (rc != QPG_OK) return rc;
+  float* kn = scratch + (size_t)M * K;
+  vq_code_norms_kernel<<<(unsigned)((K + 127) / 128), 128, 0, (cudaStream_t)stream>>>(codebook, D, K, kn);
+  QPG_LAUNCH_CHECK();
+  const size_t smem = (size_t)K * sizeof(float);
+  vq_select_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, smem, (cudaStream_t)stream>>>(x, codebook, scratch, kn, M, D,
+                                                                                         K, idx_out, min_out);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

@@ -176,16 +176,22 @@ class _TcConv:
     """One launch of qpg_conv1d_taps_tf32.  `w_taps` is a list of [C_out, C_in] matrices (one per
     tap); they are stored [n_taps][N_pad][K_pad] zero padded, K-major, as the UMMA B operand."""
 
-    def __init__(self, w_taps, bias, row_offset, chan_offset, device):
+    def __init__(self, w_taps, bias, row_offset, chan_offset, device, split=False):
+        """split: 3xTF32 (float32-accurate products): weights stored as a TF32 part and a residual part."""
         c_out, c_in = w_taps[0].shape
         self.c_in, self.c_out, self.n_taps = c_in, c_out, len(w_taps)
         self.K_pad = _round_up(c_in, 4)
-        self.BN = min(256, _round_up(c_out, 16))
+        self.BN = min(128 if split else 256, _round_up(c_out, 16))
         self.N_pad = _round_up(c_out, self.BN)
         w = torch.zeros((self.n_taps, self.N_pad, self.K_pad), dtype=torch.float32, device=device)
         for i, m in enumerate(w_taps):
             w[i, :c_out, :c_in] = m.to(device=device, dtype=torch.float32)
         self.w = w.contiguous()
+        self.split = split
+        if split:
+            mask = torch.tensor(-8192, dtype=torch.int32, device=device)              # 0xffffe000
+            self.w_hi = (self.w.view(torch.int32) & mask).view(torch.float32).contiguous()
+            self.w_lo = ((self.w - self.w_hi).view(torch.int32) & mask).view(torch.float32).contiguous()
         self.bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
         self.row_offset, self.chan_offset = list(row_offset), list(chan_offset)
 
@@ -201,13 +207,18 @@ class _TcConv:
         d.out_rows_per_item = out_rows_per_item if out_rows_per_item is not None else n_out
         d.out_ld = out_ld if out_ld is not None else self.c_out
         d.out_chan_offset = out_chan_offset
-        _lib.check(lib.qpg_conv1d_taps_tf32(d, _lib.ptr(x), _lib.ptr(self.w), _lib.ptr(self.bias), _lib.ptr(residual),
-                                            _lib.ptr(out), _lib.ptr(out_relu), _lib.stream_ptr()),
-                   "qpg_conv1d_taps_tf32")
+        if self.split:
+            _lib.check(lib.qpg_conv1d_taps_3xtf32(d, _lib.ptr(x), _lib.ptr(self.w_hi), _lib.ptr(self.w_lo),
+                                                  _lib.ptr(self.bias), _lib.ptr(residual), _lib.ptr(out),
+                                                  _lib.ptr(out_relu), _lib.stream_ptr()), "qpg_conv1d_taps_3xtf32")
+        else:
+            _lib.check(lib.qpg_conv1d_taps_tf32(d, _lib.ptr(x), _lib.ptr(self.w), _lib.ptr(self.bias), _lib.ptr(residual),
+                                                _lib.ptr(out), _lib.ptr(out_relu), _lib.stream_ptr()),
+                       "qpg_conv1d_taps_tf32")
 
 
 class _TcResnet:
-    def __init__(self, sd, prefix, depth, growth, reverse, device):
+    def __init__(self, sd, prefix, depth, growth, reverse, device, split=False):
         dil = [growth ** d for d in range(depth)]
         if reverse:
             dil = dil[::-1]
@@ -215,8 +226,8 @@ class _TcResnet:
         for d in range(depth):
             p = f"{prefix}.model.{d}.model"
             w3, b3, w1, b1 = sd[p + ".1.weight"], sd[p + ".1.bias"], sd[p + ".3.weight"], sd[p + ".3.bias"]
-            conv3 = _TcConv([w3[:, :, k] for k in range(3)], b3, [-dil[d], 0, dil[d]], [0, 0, 0], device)
-            conv1 = _TcConv([w1[:, :, 0]], b1, [0], [0], device)
+            conv3 = _TcConv([w3[:, :, k] for k in range(3)], b3, [-dil[d], 0, dil[d]], [0, 0, 0], device, split)
+            conv1 = _TcConv([w1[:, :, 0]], b1, [0], [0], device, split)
             self.blocks.append((conv3, conv1))
 
     def __call__(self, x_raw, x_relu):
@@ -236,7 +247,7 @@ class _TcResnet:
 class TcEncoder:
     """Encoder on tensor cores; the stride-2 k4 convolutions read the paired-frame view [B, T/2, 2C]."""
 
-    def __init__(self, sd, hps, device):
+    def __init__(self, sd, hps, device, split=False):
         down_t, s = hps.downs_t[0], hps.strides_t[0]
         assert s == 2
         pre = "encoders.0.level_blocks.0.model"
@@ -247,10 +258,10 @@ class TcEncoder:
             cp = _round_up(c_in, 4)                                              # channels of the (padded) input
             self.c_pad.append(cp)
             # t_in = 2t - 1 + k: k=0 -> pair t-1 second half, k=1 -> pair t first half, k=2 -> second half, k=3 -> pair t+1
-            self.downs.append(_TcConv([w[:, :, k] for k in range(4)], b, [-1, 0, 0, 1], [cp, 0, cp, 0], device))
-            self.res.append(_TcResnet(sd, f"{pre}.{i}.1", hps.depth, hps.dilation_growth_rate, False, device))
+            self.downs.append(_TcConv([w[:, :, k] for k in range(4)], b, [-1, 0, 0, 1], [cp, 0, cp, 0], device, split))
+            self.res.append(_TcResnet(sd, f"{pre}.{i}.1", hps.depth, hps.dilation_growth_rate, False, device, split))
         w, b = sd[f"{pre}.{down_t}.weight"], sd[f"{pre}.{down_t}.bias"]
-        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device, split)
 
     def __call__(self, x):
         B, T, Cc = x.shape
@@ -270,22 +281,22 @@ class TcEncoder:
 
 
 class TcDecoder:
-    def __init__(self, sd, hps, device):
+    def __init__(self, sd, hps, device, split=False):
         down_t, s = hps.downs_t[0], hps.strides_t[0]
         assert s == 2
         pre = "decoders.0.level_blocks.0.model"
         w, b = sd[f"{pre}.0.weight"], sd[f"{pre}.0.bias"]
-        self.inp = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+        self.inp = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device, split)
         self.res, self.up_even, self.up_odd = [], [], []
         for i in range(down_t):
             self.res.append(_TcResnet(sd, f"{pre}.{i + 1}.0", hps.depth, hps.dilation_growth_rate,
-                                      hps.vqvae_reverse_decoder_dilation, device))
+                                      hps.vqvae_reverse_decoder_dilation, device, split))
             w, b = sd[f"{pre}.{i + 1}.1.weight"], sd[f"{pre}.{i + 1}.1.bias"]    # [C_in, C_out, 4]
             wt = lambda k: w[:, :, k].t()
-            self.up_even.append(_TcConv([wt(1), wt(3)], b, [0, -1], [0, 0], device))
-            self.up_odd.append(_TcConv([wt(0), wt(2)], b, [1, 0], [0, 0], device))
+            self.up_even.append(_TcConv([wt(1), wt(3)], b, [0, -1], [0, 0], device, split))
+            self.up_odd.append(_TcConv([wt(0), wt(2)], b, [1, 0], [0, 0], device, split))
         w, b = sd["decoders.0.out.weight"], sd["decoders.0.out.bias"]
-        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device)
+        self.out = _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], device, split)
 
     def __call__(self, x):
         B, T, Cc = x.shape
@@ -310,8 +321,8 @@ class TcDecoder:
 class BottleneckBlock:
     """Inference half of bottleneck.py:15-154 (quantise / dequantise / encode / decode)."""
 
-    def __init__(self, k_bins, emb_width, mu=0.99, device=None):
-        self.k_bins, self.emb_width, self.mu = k_bins, emb_width, mu
+    def __init__(self, k_bins, emb_width, mu=0.99, device=None, fast=True):
+        self.k_bins, self.emb_width, self.mu, self.fast = k_bins, emb_width, mu, fast
         self.device = torch.device(device if device is not None else "cuda")
         self.k = torch.zeros((k_bins, emb_width), dtype=torch.float32, device=self.device)   # bottleneck.py:28
 
@@ -322,8 +333,15 @@ class BottleneckBlock:
         M = x.shape[0]
         x_l = torch.empty((M,), dtype=torch.int64, device=x.device)
         mind = torch.empty((M,), dtype=torch.float32, device=x.device)
-        _lib.check(lib.qpg_vq_argmin_f32(_lib.ptr(x), _lib.ptr(self.k), M, self.emb_width, self.k_bins, _lib.ptr(x_l),
-                                         _lib.ptr(mind), _lib.stream_ptr()), "qpg_vq_argmin_f32")
+        if self.fast and self.emb_width % 4 == 0 and self.k_bins % 16 == 0 and M > 0:
+            # tensor-core filter + exact re-evaluation: same indices as the float64 kernel below
+            scratch = torch.empty(((M + 1) * self.k_bins,), dtype=torch.float32, device=x.device)
+            _lib.check(lib.qpg_vq_argmin_fast(_lib.ptr(x), _lib.ptr(self.k), M, self.emb_width, self.k_bins,
+                                              _lib.ptr(scratch), _lib.ptr(x_l), _lib.ptr(mind), _lib.stream_ptr()),
+                       "qpg_vq_argmin_fast")
+        else:
+            _lib.check(lib.qpg_vq_argmin_f32(_lib.ptr(x), _lib.ptr(self.k), M, self.emb_width, self.k_bins, _lib.ptr(x_l),
+                                             _lib.ptr(mind), _lib.stream_ptr()), "qpg_vq_argmin_f32")
         return x_l, torch.mean(mind)
 
     def dequantise(self, x_l):
@@ -350,7 +368,8 @@ class VQVAE:
     """Inference surface of models/vqvae.py:52-181 (levels = 1)."""
 
     def __init__(self, hps, input_dim=72, device=None, precision=0, use_graph=True, max_graphs=8):
-        """precision 0 = float32 FFMA (index-parity mode), 1 = tcgen05 TF32 tensor cores (fast mode)."""
+        """precision 0 = float32 FFMA, 2 = 3xTF32 on the tcgen05 tensor cores (float32-accurate products: the
+        index-parity modes), 1 = plain TF32 tensor cores (fast mode, ~1e-3 relative)."""
         assert hps.levels == 1, "the reference config uses one level (codebook.yml:3)"
         self.use_graph, self.max_graphs, self._graphs = use_graph, max_graphs, {}
         _lib.load()
@@ -369,9 +388,9 @@ class VQVAE:
     def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
         sd = _strip_module(state_dict)
         self._graphs = {}
-        if self.precision == 1:
-            self.encoder = TcEncoder(sd, self.hps, self.device)
-            self.decoder = TcDecoder(sd, self.hps, self.device)
+        if self.precision in (1, 2):
+            self.encoder = TcEncoder(sd, self.hps, self.device, split=self.precision == 2)
+            self.decoder = TcDecoder(sd, self.hps, self.device, split=self.precision == 2)
         else:
             self.encoder = Encoder(sd, self.hps, self.device, self.precision)
             self.decoder = Decoder(sd, self.hps, self.device, self.precision)

@@ -56,6 +56,31 @@ def test_quantise_indices_exact(M):
     assert torch.equal(back.cpu()[0], k[got])
 
 
+@pytest.mark.parametrize("M", [1, 30, 127, 960, 4099, 20000])
+def test_quantise_fast_path_equals_float64_kernel(M):
+    """tensor-core filter + exact re-evaluation (qpg_vq_argmin_fast) == float64 kernel (qpg_vq_argmin_f32): the same
+    indices and bit-identical minimum distances, duplicate codes and exact hits included"""
+    from qpgesture_b200.vqvae import BottleneckBlock
+
+    g = torch.Generator().manual_seed(100 + M)
+    k = torch.randn((512, 512), generator=g)
+    x = torch.randn((M, 512), generator=g)
+    k[300] = k[200]                                    # duplicate code: first index must win
+    x[0] = k[200]
+    if M > 3:
+        x[1] = k[77] * 3.0                             # scaled latent
+        x[2] = 0.0                                     # zero latent: the smallest-norm code wins
+    res = {}
+    for fast in (True, False):
+        blk = BottleneckBlock(512, 512, device="cuda", fast=fast)
+        blk.k = k.cuda().contiguous()
+        x_l, fit = blk.quantise(x.cuda())
+        res[fast] = (x_l.cpu(), float(fit))
+    assert torch.equal(res[True][0], res[False][0])
+    assert res[True][1] == res[False][1]
+    assert int(res[True][0][0]) == 200
+
+
 @pytest.mark.parametrize("path", GOLDEN)
 def test_golden_encode_decode(path):
     fx, hps, sd, x = load_vq_case(path)
@@ -227,3 +252,65 @@ def test_dataset_to_code_bulk_matches_per_sequence():
     want = np.stack([vr.encode(torch.from_numpy(((p - mean) / stdc)[None]).float(), sd, hps)[0].numpy() for p in poses])
     assert got.shape == (9, 30)
     assert (got == want).mean() >= 0.99
+
+
+# ---------------------------------------------------------------------------------------------
+# 3xTF32 on the tensor cores (precision=2): float32-accurate products (x_hi*w_hi + x_lo*w_hi + x_hi*w_lo), the
+# tensor-core index-parity mode.  Same tolerances as the float32 FFMA path.
+# ---------------------------------------------------------------------------------------------
+def test_tc3_single_layers_vs_torch():
+    import torch.nn.functional as F
+
+    from qpgesture_b200.vqvae import _TcConv
+
+    g = torch.Generator().manual_seed(2)
+    dev = "cuda"
+    B, T, Cc = 7, 30, 512
+    x = torch.randn((B, T, Cc), generator=g)
+    w = torch.randn((Cc, Cc, 3), generator=g) * 0.03
+    b = torch.randn((Cc,), generator=g)
+    want = x + F.conv1d(x.double().permute(0, 2, 1), w.double(), b.double(), padding=9, dilation=9).permute(0, 2, 1)
+    conv = _TcConv([w[:, :, k] for k in range(3)], b, [-9, 0, 9], [0, 0, 0], dev, split=True)
+    xd = x.to(dev)
+    raw, relu = torch.empty_like(xd), torch.empty_like(xd)
+    conv(xd, B, T, Cc, T, out=raw, out_relu=relu, residual=xd)
+    assert _rel_err(raw.cpu().double(), want) < 3e-6, _rel_err(raw.cpu().double(), want)
+    assert torch.equal(relu, raw.clamp_min(0))
+    B, T, Ci, Co = 2, 240, 135, 512                            # stride-2 k4 on the paired view, ragged K (136)
+    x = torch.randn((B, T, Ci), generator=g)
+    w = torch.randn((Co, Ci, 4), generator=g) * 0.05
+    b = torch.randn((Co,), generator=g)
+    want = F.conv1d(x.double().permute(0, 2, 1), w.double(), b.double(), stride=2, padding=1).permute(0, 2, 1)
+    xp = F.pad(x, (0, 1)).contiguous().to(dev)
+    conv = _TcConv([w[:, :, k] for k in range(4)], b, [-1, 0, 0, 1], [136, 0, 136, 0], dev, split=True)
+    out = torch.empty((B, T // 2, Co), device=dev)
+    conv(xp, B, T // 2, 272, T // 2, out=out)
+    assert _rel_err(out.cpu().double(), want) < 3e-6, _rel_err(out.cpu().double(), want)
+    w = torch.randn((135, 512, 3), generator=g) * 0.03          # 512 -> 135, scalar-store epilogue
+    b = torch.randn((135,), generator=g)
+    x = torch.randn((3, 60, 512), generator=g)
+    want = F.conv1d(x.double().permute(0, 2, 1), w.double(), b.double(), padding=1).permute(0, 2, 1)
+    out = torch.empty((3, 60, 135), device=dev)
+    _TcConv([w[:, :, k] for k in range(3)], b, [-1, 0, 1], [0, 0, 0], dev, split=True)(x.to(dev), 3, 60, 512, 60, out=out)
+    assert _rel_err(out.cpu().double(), want) < 3e-6, _rel_err(out.cpu().double(), want)
+
+
+@pytest.mark.parametrize("path", GOLDEN)
+def test_tc3_encode_decode_vs_golden(path):
+    from qpgesture_b200.vqvae import VQVAE
+
+    fx, hps, sd, x = load_vq_case(path)
+    model = VQVAE(hps, 135, device="cuda", precision=2).load_state_dict(sd)
+    lat = model.latents(x).cpu().numpy().reshape(-1, hps.emb_width)
+    assert np.allclose(lat, fx["latents"], rtol=0, atol=2e-4), np.abs(lat - fx["latents"]).max()
+    codes = model.encode(x)[0].cpu().numpy()
+    k = sd["bottleneck.level_blocks.0.k"]
+    _, _, dist = vr.quantise(torch.from_numpy(fx["latents"]), k)
+    d_sorted, _ = torch.sort(dist, dim=1)
+    margin = (d_sorted[:, 1] - d_sorted[:, 0]).numpy().reshape(codes.shape)
+    bad = codes != fx["codes"]
+    # identical indices; a flip is tolerated only where the reference's own float32 margin is below its noise
+    assert not (bad & (margin > 1e-4)).any(), f"{int(bad.sum())} mismatches, margins {margin[bad][:8]}"
+    assert int(bad.sum()) <= 1, f"{int(bad.sum())} mismatches, margins {margin[bad][:8]}"
+    dec = model.decode([torch.from_numpy(fx["codes"])]).cpu().numpy()
+    assert np.allclose(dec, fx["decoded"], rtol=0, atol=2e-4), np.abs(dec - fx["decoded"]).max()

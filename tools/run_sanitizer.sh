@@ -1,0 +1,27 @@
+#!/bin/bash
+# compute-sanitizer memcheck + racecheck over small invocations of every hand-written kernel family
+# (scan / fused scan / Levenshtein / tail of round 1, the int8-sliced tcgen05 scan + bins + resolve + lookup + walk,
+# conv_tc).  Summaries go to gpurun_out/sanitizer_*.txt; copy them to profiles/ after reading.
+set -u
+OUT=${1:-gpurun_out}
+mkdir -p "$OUT"
+SEL='test_tensor_core_scan_equals_cuda_core_reference and (128-128 or 1000-384) or test_sliced_tables_vs_float64 and 1000-384 or test_lookup_walk_equals_round1_tail or test_resolve_merges_row_shards'
+SEL_OLD='test_cosine_minbycode_vs_oracle and 1000-384 or test_fused_two_block_scan_equals_separate_scans and 77-128 or test_levenshtein_minbycode_vs_oracle and 500-4 or test_rank512_stable'
+SEL_VQ='test_tc_single_layers_vs_torch or test_quantise_indices_exact'
+for tool in memcheck racecheck; do
+  for name in sliced old vq; do
+    case $name in
+      sliced) files=tests/test_sliced_gpu.py; sel="$SEL";;
+      old) files=tests/test_matcher_gpu.py; sel="$SEL_OLD";;
+      vq) files=tests/test_vqvae_gpu.py; sel="$SEL_VQ";;
+    esac
+    log="$OUT/sanitizer_${tool}_${name}.txt"
+    timeout 900 compute-sanitizer --tool $tool --print-limit 20 --error-exitcode 99 \
+      python -m pytest $files -q -x -k "$sel" > "$log.full" 2>&1
+    rc=$?
+    { echo "# compute-sanitizer --tool $tool  python -m pytest $files -k \"$sel\"   (exit code $rc)";
+      grep -E "passed|failed|error|ERROR SUMMARY|RACECHECK SUMMARY|Invalid|hazard|Race" "$log.full" | tail -25; } > "$log"
+    rm -f "$log.full.tmp"
+  done
+done
+tail -n 4 "$OUT"/sanitizer_*.txt
