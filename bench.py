@@ -262,43 +262,78 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------ VQ-VAE (BASELINE.json configs[1], informational)
-def vqvae_block(dev, B=4096, T=8):
-    """encode -> quantise -> decode of synthetic 8-frame pose batches on the tcgen05 TF32 path (random-init
-    weights of the codebook.yml architecture), index agreement against the float32 FFMA parity path."""
+def vqvae_block(dev, peaks, B=4096, T=8):
+    """encode -> quantise -> decode of synthetic 8-frame pose batches (random-init weights of the codebook.yml
+    architecture): TF32 and 3xTF32 on the tcgen05 tensor cores, float32 FFMA, and the same stacks as stock PyTorch
+    modules (cuDNN, TF32 allowed) on the same GPU; code-index mismatches against the float32 FFMA path."""
     import torch
+    import torch.nn.functional as F
     from qpgesture_b200.synth import random_vqvae_state_dict, vqvae_hps
     from qpgesture_b200.vqvae import VQVAE
 
     hps = vqvae_hps()
     sd = random_vqvae_state_dict(hps, 135, seed=0, codebook_seed=1)
     x = torch.randn((B, T, 135), generator=torch.Generator().manual_seed(0)).to(dev)
-    out = {}
-    codes = {}
-    for prec, name in ((1, "tf32_tcgen05"), (0, "fp32_ffma")):
-        m = VQVAE(hps, 135, device=dev, precision=prec).load_state_dict(sd)
-        reps = 10 if prec == 1 else 2
+    tf32_peak = float(peaks.get("bf16_tflops", 1590.0)) / 2.0          # dense TF32 = half the bf16 rate
+    out, codes = {}, {}
+
+    def timed(fn, reps):
         for _ in range(2):
-            zs = m.encode(x)
-            m.decode(zs)
+            r = fn()
         torch.cuda.synchronize()
-        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
-            zs = m.encode(x)
+            r = fn()
         e1.record()
-        for _ in range(reps):
-            m.decode(zs)
-        e2.record()
         torch.cuda.synchronize()
-        enc_ms, dec_ms = e0.elapsed_time(e1) / reps, e1.elapsed_time(e2) / reps
+        return e0.elapsed_time(e1) / reps, r
+    for prec, name in ((1, "tf32_tcgen05"), (2, "3xtf32_tcgen05"), (0, "fp32_ffma")):
+        m = VQVAE(hps, 135, device=dev, precision=prec).load_state_dict(sd)
+        reps = 10 if prec else 2
+        enc_ms, zs = timed(lambda: m.encode(x), reps)
+        dec_ms, _ = timed(lambda: m.decode(zs), reps)
         codes[name] = zs[0]
+        ef, df = 1.6235 * B * T / 240 / enc_ms, 1.9083 * B * T / 240 / dec_ms
         out[name] = dict(encode_ms=enc_ms, decode_ms=dec_ms, codes_per_s=B * T / 8 / enc_ms * 1e3,
-                         decoded_frames_per_s=B * T / dec_ms * 1e3,
-                         encode_tflops=1.6235 * B * T / 240 / enc_ms, decode_tflops=1.9083 * B * T / 240 / dec_ms)
-    neq = int((codes["tf32_tcgen05"] != codes["fp32_ffma"]).sum())
-    out["index_mismatches_tf32_vs_fp32"] = neq
-    out["index_agreement_tf32_vs_fp32"] = 1.0 - neq / codes["fp32_ffma"].numel()
+                         decoded_frames_per_s=B * T / dec_ms * 1e3, encode_tflops=ef, decode_tflops=df)
+        if prec:
+            out[name]["encode_frac_of_tf32_peak"] = ef * (3 if prec == 2 else 1) / tf32_peak
+            out[name]["decode_frac_of_tf32_peak"] = df * (3 if prec == 2 else 1) / tf32_peak
+    for name in ("tf32_tcgen05", "3xtf32_tcgen05"):
+        out[name]["index_mismatches_vs_fp32"] = int((codes[name] != codes["fp32_ffma"]).sum())
+    out["latents"] = int(codes["fp32_ffma"].numel())
+    # stock PyTorch (cuDNN) arm, TF32 allowed, NCT layout as the reference modules (encdec.py, resnet.py)
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        torch.backends.cuda.matmul.allow_tf32 = True
+        w = {k: v.to(dev) for k, v in sd.items()}
+        down_t, depth, g = hps.downs_t[0], hps.depth, hps.dilation_growth_rate
+
+        def res(h, pre, dils):
+            for d, dil in enumerate(dils):
+                p = f"{pre}.model.{d}.model"
+                t = F.conv1d(F.relu(h), w[p + ".1.weight"], w[p + ".1.bias"], padding=dil, dilation=dil)
+                h = h + F.conv1d(F.relu(t), w[p + ".3.weight"], w[p + ".3.bias"])
+            return h
+
+        def enc():
+            h = x.permute(0, 2, 1)
+            pre = "encoders.0.level_blocks.0.model"
+            for i in range(down_t):
+                h = F.conv1d(h, w[f"{pre}.{i}.0.weight"], w[f"{pre}.{i}.0.bias"], stride=2, padding=1)
+                h = res(h, f"{pre}.{i}.1", [g ** d for d in range(depth)])
+            h = F.conv1d(h, w[f"{pre}.{down_t}.weight"], w[f"{pre}.{down_t}.bias"], padding=1)
+            hf = h.permute(0, 2, 1).reshape(-1, h.shape[1])
+            k = w["bottleneck.level_blocks.0.k"]
+            return ((hf ** 2).sum(-1, keepdim=True) - 2 * hf @ k.t() + (k ** 2).sum(-1)[None]).argmin(-1)
+        with torch.no_grad():
+            enc_ms, _ = timed(enc, 5)
+        out["torch_cudnn_tf32"] = dict(encode_ms=enc_ms, encode_tflops=1.6235 * B * T / 240 / enc_ms)
+    except Exception as e:  # noqa: BLE001
+        out["torch_cudnn_tf32"] = dict(error=f"{type(e).__name__}: {e}")
     out["shape"] = [B, T, 135]
+    out["tf32_peak_tflops"] = tf32_peak
     return out
 
 
@@ -701,7 +736,7 @@ def main():
     del plan
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_vqvae:
-        line["vqvae"] = vqvae_block(dev)
+        line["vqvae"] = vqvae_block(dev, peaks)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
     del knn, db

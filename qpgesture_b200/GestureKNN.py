@@ -752,7 +752,8 @@ def build_knn_from_files(a, mode="A", tail="auto", device=None, seq_range=None, 
     from .data_processing import load_match_inputs
 
     inp = load_match_inputs(a.train_database, a.train_codebook, a.test_data, a.train_wavlm, a.test_wavlm,
-                            a.train_wavvq, a.test_wavvq, mode=mode)
+                            a.train_wavvq, a.test_wavvq, mode=mode,
+                            device=(device if device is not None else "cuda") if seq_range is None else None)
     signature = np.load(a.codebook_signature)["signature"]
     db = MatchDatabase(mode, inp["code"], signature, phase_to_dense(inp["phase"]), inp["txt_rows"],
                        aud_rows=inp.get("aud_rows"), aud_tokens=inp.get("aud_tokens"),

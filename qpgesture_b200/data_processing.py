@@ -116,10 +116,12 @@ def load_db_codebook(data_file, codepath, test_data_path, train_wavlm, test_wavl
 
 
 def load_match_inputs(data_file, codepath, test_data_path, train_wavlm, test_wavlm, train_wavvq, test_wavvq,
-                      mode="A"):
+                      mode="A", device=None):
     """Lean loader: only what CodeKNN's shipped path reads.  Returns a dict with
     code, phase (as stored), context windows, audio window rows / tokens and the
-    per-segment queries."""
+    per-segment queries.  With `device` the WavLM interpolation + tap stacking of the DATABASE runs on the GPU
+    (qpg_stack_wavlm_rows, bit-identical to the host path) and `aud_rows` is a CUDA tensor: the [N*26, 6C] table
+    never exists in host memory."""
     from .matchdb import wavvq_tokens
 
     data = np.load(data_file, allow_pickle=True)
@@ -132,9 +134,11 @@ def load_match_inputs(data_file, codepath, test_data_path, train_wavlm, test_wav
                txt_rows=np.ascontiguousarray(ctx[:, :WINDOWS_PER_SEQ, :].reshape(n * WINDOWS_PER_SEQ, -1),
                                              dtype=np.float32))
     if mode == "A":
-        w_tr = interpolate_wavlm(np.load(train_wavlm)["wavlm"])
         w_te = interpolate_wavlm(np.load(test_wavlm)["wavlm"])
-        out["aud_rows"] = wavlm_window_rows(w_tr)
+        if device is not None:
+            out["aud_rows"] = wavlm_rows_on_device(np.load(train_wavlm)["wavlm"], "window", device)
+        else:
+            out["aud_rows"] = wavlm_window_rows(interpolate_wavlm(np.load(train_wavlm)["wavlm"]))
         out["aud_q"] = wavlm_query_rows(w_te)                              # [M, 8, 6C]
         T = w_te.shape[1]
         i_list = list(range(0, T, STEP_SZ * (T // num_frames_code)))

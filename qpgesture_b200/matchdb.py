@@ -80,12 +80,17 @@ def phase_to_dense(phase) -> np.ndarray:
         assert ph.ndim == 4 and ph.shape[2] == 4, "dense phase must be [N,240,4,8]"
         return np.ascontiguousarray(np.concatenate((ph[:, :, 0, :], ph[:, :, 2, :]), axis=2))
     n, t = phase.shape[0], phase.shape[1]
-    out = np.empty((n, t, 16), dtype=np.float32)
-    for i in range(n):
-        for j in range(t):
-            out[i, j, :8] = phase[i, j, 0].detach().cpu().numpy().reshape(-1)
-            out[i, j, 8:] = phase[i, j, 2].detach().cpu().numpy().reshape(-1)
-    return out
+    # the reference pickles one (1, 8, 1) tensor per (sequence, frame, column): two torch.cat calls over the object
+    # cells instead of n*t*2 tensor -> numpy round trips
+    cols = []
+    for col in (0, 2):
+        cells = list(phase[:, :, col].reshape(-1))
+        if cells and isinstance(cells[0], torch.Tensor):
+            flat = torch.cat([c.detach().reshape(1, -1) for c in cells], dim=0).to(torch.float32).cpu().numpy()
+        else:
+            flat = np.stack([np.asarray(c, dtype=np.float32).reshape(-1) for c in cells]) if cells else np.zeros((0, 8), np.float32)
+        cols.append(flat.reshape(n, t, -1))
+    return np.ascontiguousarray(np.concatenate(cols, axis=2), dtype=np.float32)
 
 
 def mode_b_window_frames(n_db_frm: int = WAVVQ_FRAMES):
@@ -334,30 +339,87 @@ class MatchDatabase:
         return [j, int((self.aud_k if which == "audio" else self.txt_k)[m])]
 
 
+_PACKED_VERSION = 2
+
+
 def save_packed_db(path: str, mode: str, code, signature, phase_amp, txt_rows, aud_rows=None, aud_tokens=None,
-                   freq_code=None) -> None:
+                   freq_code=None, device=None) -> None:
     """Row 8(f).1: one-file database for the matcher.  Everything load_db_codebook + CodeKNN.__init__ derive at
-    start-up in the reference (stacked window rows, dense phase|amplitude, frequency and pose rank tables) is
-    stored ready to upload; `load_packed_db` rebuilds a MatchDatabase without touching the raw npz set."""
-    code = np.asarray(code)
-    rec = dict(mode=np.array(mode), code=code, signature=np.asarray(signature, dtype=np.float32),
-               phase_amp=np.asarray(phase_amp, dtype=np.float32), txt_rows=np.asarray(txt_rows, dtype=np.float32),
-               freq_rank=freq_rank_from_code(code if freq_code is None else freq_code),
-               pos_rank=pos_rank_table(np.asarray(signature)))
+    start-up in the reference is built ONCE on the GPU and stored in its device layout: the float32 4 KiB tiles
+    + squared norms, the int8-sliced tile images + per-row bound terms + bin order, dense phase|amplitude, the
+    frequency and pose rank tables.  `load_packed_db` then needs one host->device copy per array and no kernel."""
+    db = MatchDatabase(mode, code, signature, phase_amp, txt_rows, aud_rows=aud_rows, aud_tokens=aud_tokens,
+                       freq_code=freq_code, device=device)
+    rec = dict(version=np.array(_PACKED_VERSION), mode=np.array(mode), code=db.code_host,
+               signature=np.asarray(signature, dtype=np.float32), phase_amp=db.phase_amp_host,
+               freq_rank=db.freq_rank_host, pos_rank=db.pos_rank_host, labels=db.labels.cpu().numpy())
+
+    def put_packed(name, t: PackedRows):
+        rec[name + "_packed"], rec[name + "_sqnorm"] = t.packed.cpu().numpy(), t.sqnorm.cpu().numpy()
+        rec[name + "_shape"] = np.array([t.W, t.D], dtype=np.int64)
+
+    def put_sliced(name, t: SlicedRows):
+        rec[name + "_slices"], rec[name + "_row_info"] = t.slices.cpu().numpy(), t.row_info.cpu().numpy()
+        rec[name + "_col_exp"] = np.zeros((0,), np.int8) if t.col_exp is None else t.col_exp.cpu().numpy()
+    put_packed("txt", db.txt)
     if mode == "A":
-        rec["aud_rows"] = np.asarray(aud_rows, dtype=np.float32)
+        put_packed("aud", db.aud)
+        put_sliced("txt_s", db.txt_s)
+        put_sliced("aud_s", db.aud_s)
+        rec["order"], rec["bin_start"] = db.order.cpu().numpy(), db.bin_start.cpu().numpy()
     else:
-        rec["aud_tokens"] = np.asarray(aud_tokens, dtype=np.int64)
+        rec["tokens"] = db.tokens.cpu().numpy()
     np.savez(path, **rec)
 
 
-def load_packed_db(path: str, device=None, seq_range=None) -> "MatchDatabase":
+def load_packed_db(path: str, device=None) -> "MatchDatabase":
+    """Counterpart of save_packed_db: uploads the stored device images; no packing / slicing / sorting runs."""
+    _lib.load()
     z = np.load(path)
-    mode = str(z["mode"])
-    return MatchDatabase(mode, z["code"], z["signature"], z["phase_amp"], z["txt_rows"],
-                         aud_rows=z["aud_rows"] if mode == "A" else None,
-                         aud_tokens=z["aud_tokens"] if mode == "B" else None, freq_rank=z["freq_rank"],
-                         pos_rank=z["pos_rank"], device=device, seq_range=seq_range)
+    if int(z["version"]) != _PACKED_VERSION:
+        raise ValueError(f"{path}: packed database version {int(z['version'])}, expected {_PACKED_VERSION}")
+    dev = torch.device(device if device is not None else "cuda")
+    db = object.__new__(MatchDatabase)
+    db.mode, db.device = str(z["mode"]), dev
+    code = z["code"]
+    db.n_seq, db.code_host, db.signature = int(code.shape[0]), code.astype(np.int64), z["signature"]
+    db.seq_range, db.id_offset, db.W = (0, db.n_seq), 0, db.n_seq * WINDOWS_PER_SEQ
+    db.replicated, db.exact_offset, db.row_base = False, 0, 0
+    up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    db.labels, db.code = up(z["labels"]), up(code.astype(np.int32))
+    db.phase_amp_host = np.ascontiguousarray(z["phase_amp"], dtype=np.float32)
+    db.phase_amp = up(db.phase_amp_host)
+
+    def get_packed(name):
+        W, D = (int(v) for v in z[name + "_shape"])
+        return PackedRows(up(z[name + "_packed"]), up(z[name + "_sqnorm"]), W, D)
+
+    def get_sliced(name, D):
+        img = z[name + "_slices"]
+        buf = aligned_bytes(img.size, dev)
+        buf.copy_(torch.from_numpy(img))
+        ce = z[name + "_col_exp"]
+        return SlicedRows(buf, up(z[name + "_row_info"]), db.order, db.bin_start, up(ce) if ce.size else None, db.W, D)
+    db.txt = get_packed("txt")
+    db.aud = db.tokens = db.fused = db.aud_s = db.txt_s = None
+    if db.mode == "A":
+        db.aud = get_packed("aud")
+        db.order, db.bin_start = up(z["order"]), up(z["bin_start"])
+        db.txt_s, db.aud_s = get_sliced("txt_s", db.txt.D), get_sliced("aud_s", db.aud.D)
+        db.aud_k = [m * 6 for m in range(WINDOWS_PER_SEQ)]
+        db.n_db_frm, db.step_sz = 180, 6
+    else:
+        db.tokens = up(z["tokens"])
+        db.aud_k, _ = mode_b_window_frames()
+        db.n_db_frm, db.step_sz = WAVVQ_FRAMES, WAVVQ_FRAMES / num_frames_code
+    db.txt_k = [m * 8 for m in range(WINDOWS_PER_SEQ)]
+    db.aud_frame = torch.tensor([phase_frame(k) for k in db.aud_k], dtype=torch.int32, device=dev)
+    db.txt_frame = torch.tensor([phase_frame(k) for k in db.txt_k], dtype=torch.int32, device=dev)
+    db.freq_rank_host, db.pos_rank_host = z["freq_rank"].astype(np.int32), z["pos_rank"].astype(np.int32)
+    db.freq_rank, db.pos_rank = up(db.freq_rank_host), up(db.pos_rank_host)
+    db.pos_rank_t = up(db.pos_rank_host.T.astype(np.int16))
+    torch.cuda.synchronize(dev)
+    return db
 
 
 def new_table(Q: int, device) -> torch.Tensor:
