@@ -514,9 +514,8 @@ def sharded_sweep(args, dev, world, rank, pg_world, peak):
     tr = (_lib.SlicedTable * 1)()
     tr[0].packed, tr[0].row_sqnorm, tr[0].q, tr[0].q_info, tr[0].ldq, tr[0].D = t[0].packed, t[0].row_sqnorm, t[0].q, t[0].q_info, D, D
     tr[0].bins, tr[0].table, tr[0].ranks = _lib.dptr(parts), _lib.dptr(tab), _lib.dptr(ranks)
-    sp = _lib.stream_ptr()
-
     def step():
+        sp = _lib.stream_ptr()                            # inside: graph capture runs on its own stream
         _lib.check(lib.qpg_slice_queries_i8(job, 1, Q, n_pad, sp), "slice")
         _lib.check(lib.qpg_sliced_scan_i8(seg, 1, S.W, n_pad, Q, sp), "scan")
         _lib.check(lib.qpg_sliced_bins(t, 1, S.W, Q, w0, w0, 1, None, sp), "bins")
@@ -533,6 +532,7 @@ def sharded_sweep(args, dev, world, rank, pg_world, peak):
     run = (lambda: gr.replay()) if gr is not None else step
     steps = 20
     ms = timed_steps(run, steps, 3, dev, world)
+    sp = _lib.stream_ptr()
     pass_ms = timed_steps(lambda: lib.qpg_sliced_scan_i8(seg, 1, S.W, n_pad, Q, sp), 20, 3, dev, world)
     sacc.zero_()
     # exact float64 scan of the WHOLE table on this rank (round-1 kernel): ids must be identical
@@ -608,8 +608,6 @@ def main():
     tq_h = torch.from_numpy(tq.reshape(Q, -1)).pin_memory()
     sc_h = torch.from_numpy(sc_all[lo:lo + n_clips].copy()).pin_memory()
     sp_h = torch.from_numpy(sp_all[lo:lo + n_clips].copy()).pin_memory()
-    codes_h = torch.empty((n_clips, N_SEG, 30), dtype=torch.int64).pin_memory()
-    status_h = torch.zeros((n_clips,), dtype=torch.int32).pin_memory()
     use_graph = not args.no_graph
     plan = knn.make_plan(n_clips, N_SEG, use_graph=use_graph, engine=args.engine)
     knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, None, None)] = plan        # match_clips reuses this plan
@@ -628,12 +626,16 @@ def main():
     def step_resident():
         knn.run_plan(plan)
 
-    aq4_h, tq4_h = aq_h.view(n_clips, N_SEG, 8, -1), tq_h.view(n_clips, N_SEG, 8, -1)
+    io = knn.pinned_io(plan)                                 # pinned host mirrors of the plan's input / output buffers
+    io.qa.copy_(aq_h)
+    io.qt.copy_(tq_h)
+    io.seed_code.copy_(sc_h)
+    io.seed_phase.copy_(sp_h)
 
     def step_e2e():
-        # the public call a user makes: pinned host queries -> H2D, captured step, D2H of codes and status
-        knn.match_clips(aq4_h, tq4_h, seed_code=sc_h, seed_phase=sp_h, out=codes_h, status_out=status_h, sync=False,
-                        tail="device")
+        # the public staged call (CodeKNN.match_staged): ONE H2D copy of the step's inputs from pinned host memory,
+        # the captured step, ONE D2H copy of codes + status
+        knn.match_staged(plan, io, sync=False)
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -641,8 +643,8 @@ def main():
     warm = max(args.warmup, 3)                               # timing hygiene: never fewer than 3 warm-up steps
     ms_res = timed_steps(step_resident, args.steps, warm, dev, world)
     ms_e2e = timed_steps(step_e2e, args.steps, warm, dev, world)
-    assert int(status_h.max()) & 1 == 0, "a chosen start code had no window (IndexError in the reference)"
-    assert int(codes_h.min()) >= 0
+    assert int(io.status.max()) & 1 == 0, "a chosen start code had no window (IndexError in the reference)"
+    assert int(io.codes.min()) >= 0
 
     # ---- dominant kernel alone: ONE launch of the scan the step uses
     sp = _lib.stream_ptr()
@@ -719,8 +721,8 @@ def main():
             step_frac_of_hbm_peak=alg_bytes / (ms_res * 1e-3) / 1e9 / peak,
             non_scan_ms_per_step=ms_res - passes * pass_ms,
             e2e=dict(value=audio_seconds / (ms_e2e * 1e-3), unit="s_audio/s", ms_per_step=ms_e2e,
-                     h2d_bytes_per_step=int(aq_h.numel() * 4 + tq_h.numel() * 4 + sc_h.numel() * 4 + sp_h.numel() * 4) * world,
-                     d2h_bytes_per_step=int(codes_h.numel() * 8 + status_h.numel() * 4) * world),
+                     h2d_bytes_per_step=int(io.inp.numel()) * world, d2h_bytes_per_step=int(io.out.numel()) * world,
+                     api="CodeKNN.match_staged (one pinned H2D copy, captured step, one D2H copy)"),
             gpu_launches=int(launches_per_step * args.steps), gpu_launches_per_step=int(launches_per_step),
             roofline=dict(bound="hbm", kernel=kernel_name, achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
                           traffic=traffic, traffic_source=traffic_source, launch_ms=pass_ms,

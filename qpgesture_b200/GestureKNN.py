@@ -312,13 +312,19 @@ class CodeKNN(object):
         with torch.cuda.device(dev):
             Qt = n_tail * n_seg * STEPS_PER_SEGMENT
             p.Qt = Qt
-            if db.mode == "A":
-                p.qa = torch.zeros((Q, db.aud.D), dtype=torch.float32, device=dev)
-            else:
-                p.qa = torch.zeros((Q, 12), dtype=torch.int32, device=dev)
-            p.qt = torch.zeros((Q, db.txt.D), dtype=torch.float32, device=dev)
-            p.seed_code = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
-            p.seed_phase = torch.zeros((n_clips, 8, 16), dtype=torch.float32, device=dev)
+            # all inputs of a step live in ONE device buffer (audio queries | text queries | seed phases | seed codes)
+            # and all outputs in another (codes | status), so that a staged caller moves each with a single copy
+            a_cols, a_dt = (db.aud.D, torch.float32) if db.mode == "A" else (12, torch.int32)
+            sizes = [Q * a_cols * 4, Q * db.txt.D * 4, n_clips * 8 * 16 * 4, n_clips * 4]
+            offs = [0]
+            for sz in sizes:
+                offs.append(offs[-1] + -(-sz // 256) * 256)
+            p.inbuf = torch.zeros((offs[-1],), dtype=torch.uint8, device=dev)
+            p.in_layout = list(zip(offs[:-1], sizes))
+            p.qa = p.inbuf[offs[0]:offs[0] + sizes[0]].view(a_dt).view(Q, a_cols)
+            p.qt = p.inbuf[offs[1]:offs[1] + sizes[1]].view(torch.float32).view(Q, db.txt.D)
+            p.seed_phase = p.inbuf[offs[2]:offs[2] + sizes[2]].view(torch.float32).view(n_clips, 8, 16)
+            p.seed_code = p.inbuf[offs[3]:offs[3] + sizes[3]].view(torch.int32)
             p.fused = False
             if engine == "sliced":
                 n_pass = -(-Q // 64)
@@ -374,9 +380,11 @@ class CodeKNN(object):
             # many clips: one warp per clip walks directly (the clips hide each other's latency)
             p.trans = torch.empty((Qt, 1024), dtype=torch.int16, device=dev) \
                 if (0 < n_tail <= MAX_TABLE_WALK_CLIPS and n_seg * STEPS_PER_SEGMENT <= 104) else None
-            p.codes = torch.empty((n_tail, n_seg, num_frames_code), dtype=torch.int64, device=dev)
+            n_codes = n_tail * n_seg * num_frames_code
+            p.outbuf = torch.zeros((n_codes * 8 + n_tail * 4,), dtype=torch.uint8, device=dev)
+            p.codes = p.outbuf[:n_codes * 8].view(torch.int64).view(n_tail, n_seg, num_frames_code)
+            p.status = p.outbuf[n_codes * 8:].view(torch.int32)
             p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
-            p.status = torch.zeros((n_tail,), dtype=torch.int32, device=dev)
             p.phase = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
                 if want_phase else None
             if use_graph:
@@ -498,6 +506,36 @@ class CodeKNN(object):
         _lib.check(lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
                                       _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes),
                                       _lib.ptr(p.vote), _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
+
+    def pinned_io(self, p):
+        """Pinned host mirrors of a plan's input and output buffers with typed views (qa, qt, seed_phase,
+        seed_code; codes, status).  Fill the input views, call match_staged(p, io): one H2D copy, the captured
+        step, one D2H copy."""
+        io = SimpleNamespace(inp=torch.zeros(p.inbuf.shape, dtype=torch.uint8).pin_memory(),
+                             out=torch.zeros(p.outbuf.shape, dtype=torch.uint8).pin_memory())
+        (o0, s0), (o1, s1), (o2, s2), (o3, s3) = p.in_layout
+        io.qa = io.inp[o0:o0 + s0].view(p.qa.dtype).view(p.qa.shape)
+        io.qt = io.inp[o1:o1 + s1].view(torch.float32).view(p.qt.shape)
+        io.seed_phase = io.inp[o2:o2 + s2].view(torch.float32).view(p.seed_phase.shape)
+        io.seed_code = io.inp[o3:o3 + s3].view(torch.int32)
+        n = p.codes.numel() * 8
+        io.codes = io.out[:n].view(torch.int64).view(p.codes.shape)
+        io.status = io.out[n:].view(torch.int32)
+        return io
+
+    def match_staged(self, p, io, sync=True):
+        """One step from pinned host buffers: H2D of all inputs (one copy), the step, D2H of codes + status (one
+        copy), all on the current stream.  With sync=False the caller synchronises and MUST look at io.status
+        (bit 0: IndexError of GestureKNN.py:631 - that clip's remaining codes are -1; bit 1: tie dependent)."""
+        with torch.cuda.device(self.db.device):
+            p.inbuf.copy_(io.inp, non_blocking=True)
+            self.run_plan(p)
+            io.out.copy_(p.outbuf, non_blocking=True)
+            if sync:
+                torch.cuda.current_stream().synchronize()
+                if int(io.status.max()) & 1:
+                    raise IndexError("list index out of range")
+        return io.codes
 
     def run_plan(self, p):
         """Enqueue one step on the current stream (graph replay when the plan was captured)."""

@@ -473,6 +473,20 @@ def test_plan_engines_agree_and_match_the_reference(path):
         got[engine + "_rank"] = (p.ra.cpu().numpy().copy(), p.rt.cpu().numpy().copy())
     assert np.array_equal(got["sliced"], fx["knn_pred"])
     assert np.array_equal(got["f64"], fx["knn_pred"])
+    # the staged entry (one pinned H2D copy, the captured step, one D2H copy) gives the device tail's result
+    p = knn._plans[(1, aq.shape[0], None, "sliced")]
+    io = knn.pinned_io(p)
+    io.qa.copy_(p.qa.cpu())
+    io.qt.copy_(p.qt.cpu())
+    io.seed_code.copy_(p.seed_code.cpu())
+    io.seed_phase.copy_(p.seed_phase.cpu())
+    before = p.codes.cpu().numpy().copy()
+    p.codes.fill_(-5)
+    try:
+        staged = knn.match_staged(p, io).numpy().copy()
+        assert np.array_equal(staged, before)
+    except IndexError:
+        assert int(io.status.max()) & 1
     for k in ("_ids", "_rank"):
         for a, b in zip(got["sliced" + k], got["f64" + k]):
             assert np.array_equal(a, b)
