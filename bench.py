@@ -63,6 +63,8 @@ def parse():
     p.add_argument("--sharded-clips", type=int, default=64)
     p.add_argument("--sweep-windows", type=int, default=1 << 20)
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    p.add_argument("--pipeline", type=int, default=3,
+                   help="independent steps in flight (each on its own stream with its own buffers); 1 = one stream")
     return p.parse_args()
 
 
@@ -364,6 +366,39 @@ def timed_steps(fn, steps, warmup, dev, world):
     return ms / steps
 
 
+def timed_pipelined(run_lane, lanes, steps, warmup, dev, world):
+    """K steps issued round-robin over the lanes' streams; device time from an event on the current stream before
+    the first step (every lane waits for it) to an event after every lane has finished; max over ranks."""
+    import torch
+    import torch.distributed as dist
+    cur = torch.cuda.current_stream()
+    for i in range(warmup):
+        run_lane(lanes[i % len(lanes)])
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(cur)
+    for ln in lanes:
+        ln.stream.wait_event(e0)
+    for i in range(steps):
+        run_lane(lanes[i % len(lanes)])
+    for ln in lanes:
+        cur.wait_stream(ln.stream)
+    e1.record(cur)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms / steps
+
+
 def oracle_parity(arrs, aq, tq, seed_code, seed_phase, plan, knn):
     """The benchmarked workload against the oracle (test infrastructure, outside every timed region): the
     48 x 512 audio and text tables via sklearn's own paired cosine distance over ALL windows, and the codes via
@@ -609,12 +644,15 @@ def main():
     sc_h = torch.from_numpy(sc_all[lo:lo + n_clips].copy()).pin_memory()
     sp_h = torch.from_numpy(sp_all[lo:lo + n_clips].copy()).pin_memory()
     use_graph = not args.no_graph
-    plan = knn.make_plan(n_clips, N_SEG, use_graph=use_graph, engine=args.engine)
-    knn.__dict__.setdefault("_plans", {})[(n_clips, N_SEG, None, None)] = plan        # match_clips reuses this plan
-    plan.qa.copy_(aq_h)
-    plan.qt.copy_(tq_h)
-    plan.seed_code.copy_(sc_h)
-    plan.seed_phase.copy_(sp_h)
+    depth = max(1, args.pipeline)
+    lanes = knn.make_pipeline(n_clips, N_SEG, depth=depth, use_graph=use_graph, engine=args.engine)
+    plan = lanes[0].plan
+    for ln in lanes:                                         # every lane matches the same batch of clips
+        ln.io.qa.copy_(aq_h)
+        ln.io.qt.copy_(tq_h)
+        ln.io.seed_code.copy_(sc_h)
+        ln.io.seed_phase.copy_(sp_h)
+        ln.plan.inbuf.copy_(ln.io.inp)
     torch.cuda.synchronize()
     if plan.engine == "sliced":
         plan.stats.zero_()
@@ -626,11 +664,7 @@ def main():
     def step_resident():
         knn.run_plan(plan)
 
-    io = knn.pinned_io(plan)                                 # pinned host mirrors of the plan's input / output buffers
-    io.qa.copy_(aq_h)
-    io.qt.copy_(tq_h)
-    io.seed_code.copy_(sc_h)
-    io.seed_phase.copy_(sp_h)
+    io = lanes[0].io                                         # pinned host mirrors of the plan's input / output buffers
 
     def step_e2e():
         # the public staged call (CodeKNN.match_staged): ONE H2D copy of the step's inputs from pinned host memory,
@@ -641,10 +675,18 @@ def main():
     if rank == 0:
         sampler.start()
     warm = max(args.warmup, 3)                               # timing hygiene: never fewer than 3 warm-up steps
-    ms_res = timed_steps(step_resident, args.steps, warm, dev, world)
-    ms_e2e = timed_steps(step_e2e, args.steps, warm, dev, world)
-    assert int(io.status.max()) & 1 == 0, "a chosen start code had no window (IndexError in the reference)"
-    assert int(io.codes.min()) >= 0
+    # one stream (latency of a step) and `depth` independent steps in flight (throughput of the system)
+    ms_single = timed_steps(step_resident, args.steps, warm, dev, world)
+    ms_single_e2e = timed_steps(step_e2e, args.steps, warm, dev, world)
+    if depth > 1:
+        ms_res = timed_pipelined(knn.run_lane, lanes, args.steps, max(warm, depth), dev, world)
+        ms_e2e = timed_pipelined(knn.stage_lane, lanes, args.steps, max(warm, depth), dev, world)
+    else:
+        ms_res, ms_e2e = ms_single, ms_single_e2e
+    for ln in lanes:
+        assert int(ln.io.status.max()) & 1 == 0, "a chosen start code had no window (IndexError in the reference)"
+        assert int(ln.io.codes.min()) >= 0
+        assert torch.equal(ln.io.codes, lanes[0].io.codes), "pipeline lanes disagree"
 
     # ---- dominant kernel alone: ONE launch of the scan the step uses
     sp = _lib.stream_ptr()
@@ -679,9 +721,9 @@ def main():
         plan.sacc_t.zero_()
     # keep the same step running ~0.6 s more so that the 100 ms clock / throttle-reason sampler sees the device
     # under exactly this load.  Every rank runs the same fixed number of steps.
-    soak_steps = min(3000, int(600.0 / max(ms_res, 1e-3)) + 1)
-    for _ in range(soak_steps):
-        step_resident()
+    soak_steps = min(6000, int(600.0 / max(ms_res, 1e-3)) + 1)
+    for i in range(soak_steps):
+        knn.run_lane(lanes[i % depth])
     torch.cuda.synchronize()
     clocks = sampler.stop() if rank == 0 else None
 
@@ -712,14 +754,20 @@ def main():
             data="synthetic",
             config=dict(workload="speaker10_24s", n_seq=args.n_seq, windows=args.n_seq * 26,
                         audio_dim=6 * args.wavlm_dim, text_dim=args.ctx_dim, clips_per_gpu=n_clips, engine=plan.engine,
-                        cuda_graph=bool(use_graph), query_steps_per_rank_per_step=Q,
+                        cuda_graph=bool(use_graph), query_steps_per_rank_per_step=Q, pipeline_depth=depth,
+                        pipeline=("%d independent steps in flight, each on its own stream with its own buffers and captured "
+                                  "graph: the latency-bound small kernels of one step run beside the HBM-bound scan of the "
+                                  "next" % depth) if depth > 1 else "one stream",
                         db_bytes=int(db.W * 4 * (db.aud.D + db.txt.D)),
                         parallelism=("database replicated, clips split, no data-path collective" if world > 1 else "single GPU"),
                         l2="inputs larger than L2 (no flush needed)"),
             passes_per_step=passes, queries_per_pass=queries_per_pass,
             step_algorithmic_GBps=alg_bytes / (ms_res * 1e-3) / 1e9,
             step_frac_of_hbm_peak=alg_bytes / (ms_res * 1e-3) / 1e9 / peak,
-            non_scan_ms_per_step=ms_res - passes * pass_ms,
+            non_scan_ms_per_step=ms_single - passes * pass_ms,
+            single_stream=dict(ms_per_step=ms_single, value=audio_seconds / (ms_single * 1e-3), e2e_ms_per_step=ms_single_e2e,
+                               e2e_value=audio_seconds / (ms_single_e2e * 1e-3),
+                               note="latency of one step: one stream, no overlap between consecutive steps"),
             e2e=dict(value=audio_seconds / (ms_e2e * 1e-3), unit="s_audio/s", ms_per_step=ms_e2e,
                      h2d_bytes_per_step=int(io.inp.numel()) * world, d2h_bytes_per_step=int(io.out.numel()) * world,
                      api="CodeKNN.match_staged (one pinned H2D copy, captured step, one D2H copy)"),
@@ -735,7 +783,7 @@ def main():
             st = plan.stats.cpu().tolist()
             line["float64_decisions"] = dict(rows_in_bins_stage=int(st[0]), bins_in_resolve_stage=int(st[1]),
                                              steps_counted="all replays since the plan was reset")
-    del plan
+    del plan, lanes, io
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_vqvae:
         line["vqvae"] = vqvae_block(dev, peaks)

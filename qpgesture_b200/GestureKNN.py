@@ -507,6 +507,32 @@ class CodeKNN(object):
                                       _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes),
                                       _lib.ptr(p.vote), _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
 
+    def make_pipeline(self, n_clips: int, n_seg: int, depth: int = 3, **plan_kwargs):
+        """`depth` independent plans, each with its own stream, buffers, captured graph and pinned host mirrors:
+        consecutive steps (independent batches of clips) issued round-robin overlap, so the latency-bound small
+        kernels of one step run beside the HBM-bound scan of the next and the host<->device copies of a third.
+        Returns a list of lanes with .plan, .stream, .io; use run_lane / stage_lane."""
+        dev = self.db.device
+        lanes = []
+        for _ in range(depth):
+            st = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(st):
+                p = self.make_plan(n_clips, n_seg, **plan_kwargs)
+            st.synchronize()
+            lanes.append(SimpleNamespace(plan=p, stream=st, io=self.pinned_io(p)))
+        return lanes
+
+    def run_lane(self, lane):
+        """one step of a pipeline lane on the lane's stream, inputs already in the plan's device buffers"""
+        with torch.cuda.stream(lane.stream):
+            self.run_plan(lane.plan)
+
+    def stage_lane(self, lane):
+        """one step of a pipeline lane from its pinned host buffers (H2D, step, D2H) on the lane's stream; the
+        caller synchronises the lane's stream and looks at lane.io.status / lane.io.codes"""
+        with torch.cuda.stream(lane.stream):
+            self.match_staged(lane.plan, lane.io, sync=False)
+
     def pinned_io(self, p):
         """Pinned host mirrors of a plan's input and output buffers with typed views (qa, qt, seed_phase,
         seed_code; codes, status).  Fill the input views, call match_staged(p, io): one H2D copy, the captured
