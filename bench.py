@@ -63,7 +63,7 @@ def parse():
     p.add_argument("--sharded-clips", type=int, default=64)
     p.add_argument("--sweep-windows", type=int, default=1 << 20)
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
-    p.add_argument("--pipeline", type=int, default=3,
+    p.add_argument("--pipeline", type=int, default=4,
                    help="independent steps in flight (each on its own stream with its own buffers); 1 = one stream")
     return p.parse_args()
 

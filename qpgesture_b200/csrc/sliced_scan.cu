@@ -272,7 +272,7 @@ __device__ __forceinline__ UnitPos unit_pos(const ScanParams& p, long long u) {
 __global__ void __launch_bounds__(256, 1) sliced_scan_kernel(const ScanParams p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   const uint32_t b_slice_bytes = (uint32_t)p.n_pad * KBW;
-  const uint32_t stage_bytes = NS * SLICE_BYTES + NS * MAX_NPAD * KBW;      // fixed stride, 96 KiB
+  const uint32_t stage_bytes = NS * SLICE_BYTES + NS * b_slice_bytes;       // 88 KiB at 48 query steps
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * stage_bytes);
   uint64_t* empty = full + STAGES;
   uint64_t* acc_full = empty + STAGES;
@@ -960,7 +960,8 @@ extern "C" int qpg_sliced_scan_i8(const qpg_sliced_seg_t* segs, int n_segs, int6
   p.total_units = p.RT * p.nkb_total;
   int grid = sm_count();
   if ((long long)grid > p.total_units) grid = (int)p.total_units;
-  const size_t smem = (size_t)STAGES * (NS * SLICE_BYTES + NS * MAX_NPAD * KBW) + 8 * sizeof(uint64_t) + 16;
+  // sized for this pass's query count: what it leaves free lets the small kernels of other pipeline lanes co-reside
+  const size_t smem = (size_t)STAGES * (NS * SLICE_BYTES + NS * n_pad * KBW) + 8 * sizeof(uint64_t) + 16;
   QPG_CUDA(cudaFuncSetAttribute(sliced_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   sliced_scan_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(p);
   QPG_LAUNCH_CHECK();
