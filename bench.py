@@ -339,6 +339,67 @@ def vqvae_block(dev, peaks, B=4096, T=8):
     return out
 
 
+# ------------------------------------------------------------------ PAE pose2phase (informational)
+def pae_block(dev, T=3600):
+    """pose2phase of one synthetic T-frame pose sequence (60 s at 60 fps): the shared-diagonal device path against
+    (a) the same kernels run window by window without sharing and (b) the reference's formulation as stock PyTorch
+    modules on the same GPU (conv1d k=240 over the T materialised windows, cuDNN, TF32 allowed, batched - the
+    reference itself runs them one at a time).  Random weights of the PAE.py architecture."""
+    import torch
+    import torch.nn.functional as F
+    from qpgesture_b200 import PAE
+    from qpgesture_b200.synth import random_pae_state_dict
+
+    sd = random_pae_state_dict(0)
+    net = PAE.Model(device=dev).load_state_dict(sd)
+    rng = np.random.default_rng(0)
+    pose = np.cumsum(rng.standard_normal((T, 135)) * 0.5, axis=0)
+    mean, std = np.zeros(135), np.ones(135)
+
+    def timed(fn, reps):
+        for _ in range(2):
+            r = fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            r = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps, r
+    out = dict(frames=T)
+    ms, par = timed(lambda: PAE.pose2phase(net, pose, mean, std, as_device_tensor=True), 5)
+    out["shared_diagonals"] = dict(ms=ms, frames_per_s=T / ms * 1e3)
+    vel_pad = torch.zeros((T + 238, 135), dtype=torch.float32, device=dev)
+    vel_pad[120:120 + T - 1] = torch.from_numpy((pose[1:] - pose[:-1]).astype(np.float32)).to(dev)
+    win = torch.zeros((T, 135, 240), dtype=torch.float32, device=dev)
+    win[:, :, 1:] = vel_pad.unfold(0, 239, 1)[:T]
+    ms2, (lat2, par2) = timed(lambda: net.embed(win), 2)
+    out["per_window_same_kernels"] = dict(ms=ms2, frames_per_s=T / ms2 * 1e3)
+    d = (par - par2).abs()
+    d[:, 0] = torch.minimum(d[:, 0], 1 - d[:, 0])
+    out["max_abs_diff_between_the_two"] = float(d[~torch.isnan(d)].max())
+    try:
+        torch.backends.cudnn.allow_tf32 = True
+        w = {k: torch.as_tensor(v).to(dev) for k, v in sd.items()}
+
+        def bn(x, n):
+            return F.batch_norm(x, w[n + ".running_mean"], w[n + ".running_var"], w[n + ".weight"], w[n + ".bias"])
+
+        def torch_arm():
+            y = torch.tanh(bn(F.conv1d(win, w["conv1.weight"], w["conv1.bias"], padding=120), "bn_conv1"))
+            y = torch.tanh(bn(F.conv1d(y, w["conv2.weight"], w["conv2.bias"], padding=119), "bn_conv2"))
+            r = torch.fft.rfft(y, dim=2)
+            pw = r.abs()[:, :, 1:] ** 2
+            return y, pw.sum(2)
+        with torch.no_grad():
+            ms3, _ = timed(torch_arm, 2)
+        out["torch_cudnn_per_window"] = dict(ms=ms3, frames_per_s=T / ms3 * 1e3)
+    except Exception as e:  # noqa: BLE001
+        out["torch_cudnn_per_window"] = dict(error=f"{type(e).__name__}: {e}")
+    return out
+
+
 # ------------------------------------------------------------------ helpers
 def timed_steps(fn, steps, warmup, dev, world):
     import torch
@@ -787,6 +848,10 @@ def main():
     torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_vqvae:
         line["vqvae"] = vqvae_block(dev, peaks)
+        try:
+            line["pae_pose2phase"] = pae_block(dev)
+        except Exception as e:  # noqa: BLE001
+            line["pae_pose2phase"] = dict(error=f"{type(e).__name__}: {e}")
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, args.cpu_sample_seq, 1)
     del knn, db

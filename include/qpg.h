@@ -370,6 +370,30 @@ int qpg_conv1d_taps_tf32(const qpg_conv_tc_desc_t* desc, const float* in, const 
 int qpg_conv1d_taps_3xtf32(const qpg_conv_tc_desc_t* desc, const float* in, const float* w_hi, const float* w_lo,
                            const float* bias, const float* residual, float* out, float* out_relu, void* stream);
 
+/* ---------------- periodic auto-encoder inference: the producer of the database's phase column ----------------
+ * Reference: codebook/PAE.py:50-162 (Model.forward, eval mode), :477-508 (pose2phase).  BatchNorm (eval) and the
+ * convolution / linear bias are folded by the caller into one (scale, shift) pair per output channel:
+ *   y = act(scale[o] * sum + shift[o]).
+ *
+ * qpg_pae_sliding_conv1: first convolution + BatchNorm + tanh for ALL T windows of pose2phase at once.
+ *   vel_pad [T + 238, C] float32 is the zero-padded frame-difference sequence (PAE.py:481-482); window i is rows
+ *   i .. i+238 behind one zero frame (:491-499).  w [O, C, K] (conv1.weight).  h1 [T, O, K + 1] receives
+ *   tanh(bn(conv1(window_i))).  Shared work between overlapping windows is computed once (float64 prefix sums over
+ *   the kernel taps); built for K = 240, O = 15, C <= 135.
+ * qpg_pae_conv1d: plain batched Conv1d (cross-correlation, zeros padding, stride 1): x [B, Ci, Lin], w [Co, Ci, K],
+ *   out [B, Co, Lin + 2 pad - K + 1]; act 0 = none, 1 = tanh.  K a multiple of 4, at most 256.
+ * qpg_pae_params: latent [B, E, T] -> params [B, 4, E] = (phase, frequency, amplitude, offset) per channel
+ *   (PAE.py:99-114 from the power spectrum without the DC bin, float64 DFT; :132-136 phase = atan2 of the folded
+ *   Linear(T, 2) outputs with the model's own atan2 :92-97, in turns).  fcw [E, 2, T], fc_scale / fc_shift [E, 2],
+ *   freqs [T / 2] and time_scale as the model holds them (:60-65).
+ */
+int qpg_pae_sliding_conv1(const float* vel_pad, const float* w, const float* scale, const float* shift, int T, int C,
+                          int O, int K, float* h1, void* stream);
+int qpg_pae_conv1d(const float* x, const float* w, const float* scale, const float* shift, int B, int Ci, int Lin,
+                   int Co, int K, int pad, int act, float* out, void* stream);
+int qpg_pae_params(const float* latent, const float* fcw, const float* fc_scale, const float* fc_shift,
+                   const float* freqs, float time_scale, int B, int E, int T, float* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

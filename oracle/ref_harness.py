@@ -172,3 +172,60 @@ def import_vqvae(quiet=True):
 
 def release_vqvae():
     _purge(_VQ_LOCAL_MODULES)
+
+
+_PAE_LOCAL_MODULES = ("PAE", "Library", "data_loader", "configs", "easydict", "configargparse")
+
+
+def import_pae(quiet=True):
+    """Import the reference's codebook/PAE.py on CPU.  Its module-level imports pull in plotting, the AdamWR
+    optimiser, the lmdb loader and easydict, none of which `Model` / `pose2phase` (PAE.py:50-162, 477-508) use:
+    they are replaced by empty stub modules (matplotlib, lmdb and easydict are not installed here).
+    `pose2phase` reads the module global `mydevice` that only `__main__` sets (:513): patched to CPU."""
+    import torch
+
+    if not available():
+        raise RuntimeError("reference not present at " + REF_ROOT)
+    _purge(_PAE_LOCAL_MODULES)
+    saved = {}
+
+    def stub(name, **attrs):
+        saved[name] = sys.modules.get(name)
+        m = types.ModuleType(name)
+        m.__path__ = []
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[name] = m
+        return m
+
+    stub("Library")
+    stub("Library.Utility")
+    stub("Library.Plotting")
+    stub("Library.AdamWR")
+    stub("Library.AdamWR.adamw")
+    stub("Library.AdamWR.cyclic_scheduler")
+    if "matplotlib" not in sys.modules:
+        try:
+            importlib.import_module("matplotlib.pyplot")
+        except Exception:
+            stub("matplotlib")
+            stub("matplotlib.pyplot")
+    stub("data_loader")
+    stub("data_loader.lmdb_data_loader", TrinityDataset=object)
+    stub("easydict", EasyDict=dict)
+    stub("configs")
+    stub("configs.parse_args", parse_args=lambda: None)
+    old_path = list(sys.path)
+    sys.path.insert(0, REF_CODEBOOK_DIR)
+    try:
+        with _quiet(quiet):
+            mod = importlib.import_module("PAE")
+    finally:
+        sys.path[:] = old_path
+    mod.mydevice = torch.device("cpu")
+    return mod
+
+
+def release_pae():
+    _purge(_PAE_LOCAL_MODULES + ("matplotlib",) if "matplotlib" in sys.modules and
+           not hasattr(sys.modules["matplotlib"], "__version__") else _PAE_LOCAL_MODULES)

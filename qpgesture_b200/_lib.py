@@ -100,6 +100,9 @@ SIGNATURES = {
     "qpg_conv1d_taps_f32": (_INT, [C.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
     "qpg_conv1d_taps_tf32": (_INT, [C.POINTER(ConvTcDesc), _P, _P, _P, _P, _P, _P, _P]),
     "qpg_conv1d_taps_3xtf32": (_INT, [C.POINTER(ConvTcDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
+    "qpg_pae_sliding_conv1": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _INT, _P, _P]),
+    "qpg_pae_conv1d": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _INT, _INT, _INT, _INT, _P, _P]),
+    "qpg_pae_params": (_INT, [_P, _P, _P, _P, _P, C.c_float, _INT, _INT, _INT, _P, _P]),
 }
 
 

@@ -167,3 +167,35 @@ def random_vqvae_state_dict(hps, input_dim=135, seed=0, codebook_seed=1, codeboo
     sd["bottleneck.level_blocks.0.k"] = codebook_scale * torch.randn(
         (hps.l_bins, e), generator=torch.Generator().manual_seed(codebook_seed))
     return sd
+
+
+def random_pae_state_dict(seed=0, input_channels=135, embedding_channels=8, time_range=240):
+    """Deterministic periodic auto-encoder weights in the reference's state-dict layout (PAE.py:50-90; the
+    repository ships no checkpoint): convolutions scaled so that the tanh layers are not saturated, BatchNorm with
+    non-trivial running statistics."""
+    g = torch.Generator().manual_seed(seed)
+    mid = input_channels // 9
+    sd = {}
+
+    def conv(name, co, ci, gain):
+        sd[name + ".weight"] = torch.randn((co, ci, time_range), generator=g) * gain / (ci * time_range) ** 0.5
+        sd[name + ".bias"] = torch.randn((co,), generator=g) * 0.1
+
+    def bn(name, c):
+        sd[name + ".weight"] = torch.rand((c,), generator=g) + 0.5
+        sd[name + ".bias"] = torch.randn((c,), generator=g) * 0.1
+        sd[name + ".running_mean"] = torch.randn((c,), generator=g) * 0.1
+        sd[name + ".running_var"] = torch.rand((c,), generator=g) + 0.5
+
+    conv("conv1", mid, input_channels, 1.5)
+    bn("bn_conv1", mid)
+    conv("conv2", embedding_channels, mid, 2.5)
+    bn("bn_conv2", embedding_channels)
+    for i in range(embedding_channels):
+        sd[f"fc.{i}.weight"] = torch.randn((2, time_range), generator=g) / time_range ** 0.5
+        sd[f"fc.{i}.bias"] = torch.randn((2,), generator=g) * 0.1
+        bn(f"bn.{i}", 2)
+    conv("deconv1", mid, embedding_channels, 2.0)
+    bn("bn_deconv1", mid)
+    conv("deconv2", input_channels, mid, 1.0)
+    return sd
