@@ -113,6 +113,150 @@ __global__ void __launch_bounds__(THREADS)
   }
 }
 
+// ---- few latents (one 4-s sequence = 30): ONE launch, no key buffer ------------------------------------------
+// A cluster of 8 CTAs owns SM_TM latents; each CTA takes 64 codes (one per thread), so a 30-latent call spreads
+// over 120 CTAs instead of 8.  Block minima of the lexicographic (distance, code) key go to CTA 0 of the cluster
+// through distributed shared memory, which writes idx / min directly: no init / finish kernels, no atomics.  The
+// arithmetic per (latent, code) is vq_argmin_kernel's, operation for operation (same float64 accumulation order,
+// same warp reduction for |x|^2), so the two kernels return identical bits.
+constexpr int SM_TM = 2;
+constexpr int SM_CODES = 64;     // codes (= threads) per CTA
+constexpr int SM_CLUSTER = 8;    // CTAs per cluster: up to 512 codes
+__global__ void __cluster_dims__(1, SM_CLUSTER, 1) __launch_bounds__(SM_CODES)
+    vq_argmin_small_kernel(const float* __restrict__ x, const float* __restrict__ cb, int64_t M, int D, int K,
+                           int64_t* __restrict__ idx_out, float* __restrict__ min_out) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int Dp = (D + 3) & ~3;
+  double* xs = reinterpret_cast<double*>(smem_raw);                 // [SM_TM][Dp]
+  float* xn = reinterpret_cast<float*>(xs + (size_t)SM_TM * Dp);    // [SM_TM]
+  unsigned long long* red = reinterpret_cast<unsigned long long*>(xn + 4);      // [SM_TM][2] warp minima
+  unsigned long long* gather = red + SM_TM * 2;                                 // [SM_CLUSTER][SM_TM], used in CTA 0
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int64_t m0 = (int64_t)blockIdx.x * SM_TM;
+  // every CTA of the cluster is running before anyone writes into CTA 0's shared memory (completed at the wait below)
+  asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+  for (int i = tid; i < SM_TM * Dp; i += SM_CODES) {
+    const int r = i / Dp, d = i - r * Dp;
+    const int64_t m = m0 + r;
+    xs[i] = (m < M && d < D) ? (double)x[m * D + d] : 0.0;
+  }
+  __syncthreads();
+  for (int r = warp; r < SM_TM; r += SM_CODES / 32) {
+    double s = 0.0;
+    for (int d = lane; d < Dp; d += 32) s = fma(xs[r * Dp + d], xs[r * Dp + d], s);
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) xn[r] = (float)s;
+  }
+  __syncthreads();
+  const int k = blockIdx.y * SM_CODES + tid;
+  unsigned long long key[SM_TM];
+#pragma unroll
+  for (int r = 0; r < SM_TM; ++r) key[r] = ~0ull;
+  if (k < K) {
+    const float* row = cb + (size_t)k * D;
+    double acc[SM_TM], kn = 0.0;
+#pragma unroll
+    for (int r = 0; r < SM_TM; ++r) acc[r] = 0.0;
+    // d ascending, four elements per step, exactly as vq_argmin_kernel; the loads run one 128-byte line (8 float4) ahead
+    auto step = [&](const float4 cv, int d) {
+      const double c0 = cv.x, c1 = cv.y, c2 = cv.z, c3 = cv.w;
+      kn = fma(c0, c0, kn);
+      kn = fma(c1, c1, kn);
+      kn = fma(c2, c2, kn);
+      kn = fma(c3, c3, kn);
+#pragma unroll
+      for (int r = 0; r < SM_TM; ++r) {
+        const double2 x01 = *reinterpret_cast<const double2*>(xs + (size_t)r * Dp + d);
+        const double2 x23 = *reinterpret_cast<const double2*>(xs + (size_t)r * Dp + d + 2);
+        double a = acc[r];
+        a = fma(x01.x, c0, a);
+        a = fma(x01.y, c1, a);
+        a = fma(x23.x, c2, a);
+        a = fma(x23.y, c3, a);
+        acc[r] = a;
+      }
+    };
+    if ((D & 31) == 0) {
+      float4 cur[8], nxt[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cur[j] = __ldg(reinterpret_cast<const float4*>(row) + j);
+      for (int d = 0; d < D; d += 32) {
+        if (d + 32 < D) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) nxt[j] = __ldg(reinterpret_cast<const float4*>(row + d + 32) + j);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) step(cur[j], d + 4 * j);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+      }
+    } else {
+      for (int d = 0; d < Dp; d += 4) {
+        float4 cv;
+        cv.x = d < D ? row[d] : 0.f;
+        cv.y = d + 1 < D ? row[d + 1] : 0.f;
+        cv.z = d + 2 < D ? row[d + 2] : 0.f;
+        cv.w = d + 3 < D ? row[d + 3] : 0.f;
+        step(cv, d);
+      }
+    }
+    const float knf = (float)kn;
+#pragma unroll
+    for (int r = 0; r < SM_TM; ++r) {
+      const float dist = __fadd_rn(__fsub_rn(xn[r], __fmul_rn(2.0f, (float)acc[r])), knf);
+      key[r] = ((unsigned long long)ordered_u32(dist) << 32) | (unsigned long long)k;
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SM_TM; ++r) {
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xffffffffu, key[r], o);
+      key[r] = other < key[r] ? other : key[r];
+    }
+    if (lane == 0) red[r * 2 + warp] = key[r];
+  }
+  __syncthreads();
+  // block minimum -> slot [my rank] of CTA 0's gather array (distributed shared memory)
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+  asm volatile("barrier.cluster.wait.aligned;" ::: "memory");
+  if (tid < SM_TM) {
+    const unsigned long long v = red[tid * 2] < red[tid * 2 + 1] ? red[tid * 2] : red[tid * 2 + 1];
+    uint32_t remote;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(gather + rank * SM_TM + tid)), "r"(0u));
+    asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(remote), "l"(v) : "memory");
+  }
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  if (rank == 0 && tid < SM_TM && m0 + tid < M) {
+    unsigned long long v = ~0ull;
+#pragma unroll
+    for (int c = 0; c < SM_CLUSTER; ++c) {
+      const unsigned long long o = gather[c * SM_TM + tid];
+      v = o < v ? o : v;
+    }
+    idx_out[m0 + tid] = (int64_t)(v & 0xffffffffull);
+    if (min_out) min_out[m0 + tid] = unordered_f32((uint32_t)(v >> 32));
+  }
+}
+
+constexpr int64_t kSmallM = 256;
+inline bool small_ok(int64_t M, int D, int K) {
+  return M <= kSmallM && K <= SM_CODES * SM_CLUSTER && (size_t)SM_TM * ((D + 3) & ~3) * sizeof(double) <= 160 * 1024;
+}
+int launch_small(const float* x, const float* cb, int64_t M, int D, int K, int64_t* idx_out, float* min_out,
+                 cudaStream_t st) {
+  const int Dp = (D + 3) & ~3;
+  const size_t smem = (size_t)SM_TM * Dp * sizeof(double) + 4 * sizeof(float) +
+                      (SM_TM * 2 + SM_CLUSTER * SM_TM) * sizeof(unsigned long long);
+  QPG_CUDA(cudaFuncSetAttribute(vq_argmin_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  dim3 grid((unsigned)((M + SM_TM - 1) / SM_TM), SM_CLUSTER);
+  vq_argmin_small_kernel<<<grid, SM_CODES, smem, st>>>(x, cb, M, D, K, idx_out, min_out);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
 // ---- fast path: tensor-core filter + exact re-evaluation of the near-minimal codes --------------------------
 // G = X * C^T comes from the tcgen05 TF32 tap-GEMM (conv1d_tc.cu, one tap).  TF32 truncates both operands to 11
 // significant bits, so |G~ - G| <= ~2^-9 * sum|x_i c_i| <= 2^-9 |x||c|; with the margin below every code whose
@@ -212,6 +356,7 @@ extern "C" int qpg_vq_argmin_f32(const float* x, const float* codebook, int64_t 
   const size_t smem = (size_t)TM * Dp * sizeof(double) + TM * sizeof(float) + 64;
   QPG_CHECK_ARG(smem <= 200 * 1024, "D too large");
   cudaStream_t st = (cudaStream_t)stream;
+  if (small_ok(M, D, K)) return launch_small(x, codebook, M, D, K, idx_out, min_out, st);
   // idx_out doubles as the 64-bit key buffer (ordered distance << 32 | code) until the finish kernel
   unsigned long long* keys = reinterpret_cast<unsigned long long*>(idx_out);
   vq_key_init_kernel<<<(unsigned)((M + 255) / 256), 256, 0, st>>>(keys, M);
@@ -242,6 +387,8 @@ extern "C" int qpg_vq_argmin_fast(const float* x, const float* codebook, int64_t
   if (M == 0) return QPG_OK;
   QPG_CHECK_ARG(x && codebook && idx_out && scratch, "null pointer");
   QPG_CHECK_ARG(D % 4 == 0 && K % 16 == 0 && K <= 12288 && M < (1ll << 31), "needs D % 4 == 0, K % 16 == 0");
+  // a handful of latents: the one-launch exact kernel beats three launches (GEMM, code norms, selection)
+  if (small_ok(M, D, K)) return launch_small(x, codebook, M, D, K, idx_out, min_out, (cudaStream_t)stream);
   // G[M, K] = X * C^T on the tensor cores: the latents as a one-item sequence of M frames, the codebook as the
   // (K-major) weights of a single tap
   qpg_conv_tc_desc_t d;

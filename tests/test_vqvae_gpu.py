@@ -81,6 +81,31 @@ def test_quantise_fast_path_equals_float64_kernel(M):
     assert int(res[True][0][0]) == 200
 
 
+@pytest.mark.parametrize("M", [1, 30, 255, 256])
+def test_quantise_one_launch_kernel_equals_tiled_kernel(M):
+    """M <= 256 latents take the single-launch kernel (one CTA = all codes, block reduction); the same rows inside a
+    larger call take the tiled kernel with atomics: identical indices, bit-identical minimum distances."""
+    from qpgesture_b200 import _lib
+
+    g = torch.Generator().manual_seed(7 + M)
+    k = torch.randn((512, 512), generator=g).cuda()
+    k[300] = k[200]
+    big = torch.randn((M + 300, 512), generator=g).cuda()
+    big[0] = k[200]
+    lib = _lib.load()
+    out = {}
+    for name, rows in (("small", M), ("big", M + 300)):
+        x = big[:rows].contiguous()
+        idx = torch.empty(rows, dtype=torch.int64, device="cuda")
+        mind = torch.empty(rows, dtype=torch.float32, device="cuda")
+        _lib.check(lib.qpg_vq_argmin_f32(_lib.ptr(x), _lib.ptr(k), rows, 512, 512, _lib.ptr(idx), _lib.ptr(mind),
+                                         _lib.stream_ptr()), "qpg_vq_argmin_f32")
+        out[name] = (idx[:M].cpu(), mind[:M].cpu())
+    assert torch.equal(out["small"][0], out["big"][0])
+    assert torch.equal(out["small"][1].view(torch.int32), out["big"][1].view(torch.int32))
+    assert int(out["small"][0][0]) == 200
+
+
 @pytest.mark.parametrize("path", GOLDEN)
 def test_golden_encode_decode(path):
     fx, hps, sd, x = load_vq_case(path)

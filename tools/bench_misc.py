@@ -16,6 +16,22 @@ def timed(fn, reps=20):
     e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1) / reps
 
+def timed_graph(fn, reps=20):
+    """device time per call with the host out of the loop: `reps` calls captured into one CUDA graph"""
+    st = torch.cuda.Stream()
+    with torch.cuda.stream(st):
+        fn(); fn()
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            for _ in range(reps): fn()
+        g.replay(); st.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        for _ in range(5): g.replay()
+        e1.record(st); st.synchronize()
+    return e0.elapsed_time(e1) / (5 * reps)
+
 def main():
     lib = _lib.load(); dev = torch.device("cuda"); sp = _lib.stream_ptr()
     g = torch.Generator(device=dev); g.manual_seed(0)
@@ -36,6 +52,16 @@ def main():
                    reps=20 if M < 10000 else 3)
         print(json.dumps(dict(kernel="vq_argmin_kernel", M=M, ms=ms, latents_per_s=M / ms * 1e3,
                               tflops=2 * M * 512 * 512 / ms / 1e9)), flush=True)
+        scratch = torch.empty(M * 512 + 512, device=dev)
+        idx2 = torch.empty(M, dtype=torch.int64, device=dev)
+        ms2 = timed(lambda: lib.qpg_vq_argmin_fast(_lib.ptr(x), _lib.ptr(cb), M, 512, 512, _lib.ptr(scratch), _lib.ptr(idx2),
+                                                   _lib.ptr(mind), sp), reps=20)
+        print(json.dumps(dict(kernel="vq_argmin_fast (tf32 tcgen05 filter + exact re-evaluation)", M=M, ms=ms2,
+                              latents_per_s=M / ms2 * 1e3, equal_to_exact=bool(torch.equal(idx, idx2)))), flush=True)
+        if M <= 960:
+            msg = timed_graph(lambda: lib.qpg_vq_argmin_fast(_lib.ptr(x), _lib.ptr(cb), M, 512, 512, _lib.ptr(scratch),
+                                                             _lib.ptr(idx2), _lib.ptr(mind), _lib.stream_ptr()))
+            print(json.dumps(dict(kernel="vq_argmin_fast, replayed from a CUDA graph (device time)", M=M, ms=msg)), flush=True)
     Q = 48
     tab = new_table(Q, dev); lib.qpg_table_init(_lib.ptr(tab), Q * 512, sp)
     ranks = torch.empty((Q, 512), dtype=torch.int32, device=dev)
