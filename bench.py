@@ -63,6 +63,8 @@ def parse():
     p.add_argument("--sharded-clips", type=int, default=64)
     p.add_argument("--sweep-windows", type=int, default=1 << 20)
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
+    p.add_argument("--scan-priority", type=int, default=0,
+                   help="1: the scan of every pipeline lane runs on a high-priority side stream")
     p.add_argument("--pipeline", type=int, default=4,
                    help="independent steps in flight (each on its own stream with its own buffers); 1 = one stream")
     return p.parse_args()
@@ -706,7 +708,23 @@ def main():
     sp_h = torch.from_numpy(sp_all[lo:lo + n_clips].copy()).pin_memory()
     use_graph = not args.no_graph
     depth = max(1, args.pipeline)
-    lanes = knn.make_pipeline(n_clips, N_SEG, depth=depth, use_graph=use_graph, engine=args.engine)
+    if os.environ.get("QPG_DIAG_SKIP"):
+        # diagnosis only (numbers are NOT bench values): drop stages from the captured step to see what the
+        # pipelined step time is made of, e.g. QPG_DIAG_SKIP=scan or QPG_DIAG_SKIP=small
+        skip = os.environ["QPG_DIAG_SKIP"]
+        small = ("qpg_slice_queries_i8", "qpg_sliced_bins", "qpg_sliced_resolve", "qpg_match_lookup", "qpg_match_walk")
+        names = {"scan": ("qpg_sliced_scan_i8",), "small": small}.get(skip, tuple(skip.split(",")))
+
+        class _Skip:
+            def __init__(self, inner):
+                self._inner = inner
+
+            def __getattr__(self, k):
+                return (lambda *a: 0) if k in names else getattr(self._inner, k)
+        _lib._lib = _Skip(lib)
+        args.no_parity = True
+    lanes = knn.make_pipeline(n_clips, N_SEG, depth=depth, use_graph=use_graph, engine=args.engine,
+                              **(dict(scan_priority=True) if args.scan_priority and args.engine == "sliced" else {}))
     plan = lanes[0].plan
     for ln in lanes:                                         # every lane matches the same batch of clips
         ln.io.qa.copy_(aq_h)

@@ -284,14 +284,17 @@ class CodeKNN(object):
 
     # ---- preallocated plan: the whole step as a fixed launch sequence (optionally one CUDA graph) ------
     def make_plan(self, n_clips: int, n_seg: int, tail_clips=None, use_graph: bool = True, want_phase=False,
-                  engine: Optional[str] = None):
+                  engine: Optional[str] = None, scan_priority: bool = False):
         """Static device buffers for `n_clips` clips x `n_seg` segments.  `tail_clips` = slice of the
         clips whose sequential tail this rank runs (default: all).  Fill plan.qa / plan.qt /
         plan.seed_code / plan.seed_phase, then call run_plan(plan); results land in plan.codes / plan.status.
 
         engine "sliced" (default in mode A): every query step of the batch in ONE pass over the int8-sliced
         table per 64 steps (tcgen05 kind::i8) + interval logic + float64 re-evaluation of undecided bins;
-        engine "f64": the float64 streaming scans of round 1 (4 steps per pass; the only engine of mode B)."""
+        engine "f64": the float64 streaming scans of round 1 (4 steps per pass; the only engine of mode B).
+        `scan_priority`: launch the HBM-bound scan on a high-priority side stream (a fork/join inside the captured
+        graph), so that in a pipeline of plans its persistent CTAs take freed SM resources before the small
+        kernels of the other lanes do."""
         dev, db = self.db.device, self.db
         Q = n_clips * n_seg * STEPS_PER_SEGMENT
         tc = tail_clips if tail_clips is not None else slice(0, n_clips)
@@ -387,6 +390,7 @@ class CodeKNN(object):
             p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
             p.phase = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
                 if want_phase else None
+            p.scan_stream = torch.cuda.Stream(device=dev, priority=-1) if scan_priority else None
             if use_graph:
                 self._launch_plan(p)                       # warm-up outside capture (sets function attributes)
                 torch.cuda.synchronize(dev)
@@ -440,7 +444,18 @@ class CodeKNN(object):
             segs[1].db_slices, segs[1].q_slices, segs[1].sacc, segs[1].n_kblocks = \
                 T.slices.data_ptr(), ps.qs_t.data_ptr(), p.sacc_t.data_ptr(), T.n_kblocks
             # sacc is all zero here: zero-initialised by make_plan and re-zeroed by every bins stage (consume = 1)
-            _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "qpg_sliced_scan_i8")
+            side = getattr(p, "scan_stream", None)
+            if side is None:
+                _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp), "qpg_sliced_scan_i8")
+            else:
+                cur = torch.cuda.current_stream()
+                fork, join = torch.cuda.Event(), torch.cuda.Event()
+                fork.record(cur)
+                side.wait_event(fork)
+                _lib.check(lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, _lib.stream_ptr(side)),
+                           "qpg_sliced_scan_i8")
+                join.record(side)
+                cur.wait_event(join)
             _lib.check(lib.qpg_sliced_bins(self._sliced_tables(p, ps.q0, ps.nq, ps.q0), 2, A.W, ps.nq, db.id_offset,
                                            db.row_base, 1, _lib.ptr(p.stats), sp), "qpg_sliced_bins")
         per_clip = p.n_seg * STEPS_PER_SEGMENT

@@ -10,12 +10,15 @@
 // tile is a dense TMA box and the conv zero padding is TMA's out-of-bounds zero fill
 // (3-D tensor map, box [Bbox items][Tbox frames][32 floats], SWIZZLE_128B).
 //
-// One CTA computes a 128 x BN output tile (BN <= 256, a multiple of 16):
-//   warp 0   TMA producer      cp.async.bulk.tensor (A: 3-D, B: 2-D) -> 4-stage smem ring, mbarrier full/empty
-//   warp 1   MMA issuer        one lane: 4 x tcgen05.mma.kind::tf32 (K = 8) per stage, tcgen05.commit frees the stage
-//   warp 2   TMEM allocator    128 lanes x BN columns of float32 accumulators
-//   warps 4-7 epilogue         tcgen05.ld 32x32b -> +bias, +residual -> raw and/or ReLU'd copy (the ReLU that
-//                              ResConv1DBlock applies on load is applied by the PRODUCER of an activation)
+// Persistent CTAs (one per SM) walk the 128 x BN output tiles (BN <= 256, a multiple of 16) round-robin:
+//   warp 0    TMA producer      cp.async.bulk.tensor (A: 3-D, B: 2-D) -> 4-stage smem ring, mbarrier full/empty,
+//                               running ahead across tile boundaries
+//   warp 1    MMA issuer        one lane: 4 x tcgen05.mma.kind::tf32 (K = 8) per stage, tcgen05.commit frees the stage
+//   warp 2    TMEM allocator    TWO accumulators of 128 lanes x BN float32 columns: the epilogue of tile i drains one
+//                               while the MMAs of tile i + 1 fill the other
+//   warps 4-11 epilogue         tcgen05.ld 32x32b -> shared-memory transpose -> +bias, +residual (prefetched one chunk
+//                               ahead) -> raw and/or ReLU'd copy in full 128-byte lines (the ReLU that ResConv1DBlock
+//                               applies on load is applied by the PRODUCER of an activation)
 // Replaces nn.Conv1d / nn.ConvTranspose1d at encdec.py:20,24,39,45,113 and resnet.py:33-36 in
 // "fast" mode (TF32 operands, ~1e-3 relative); the float32 FFMA path of conv1d.cu stays the parity mode.
 #include <cuda.h>
@@ -94,79 +97,127 @@ __device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// ===== epilogue: TMEM -> registers -> global (warps 4-7 of either kernel) =====
-__device__ __forceinline__ void conv_epilogue(const TcParams& p, uint32_t tmem_base, uint64_t* accum_full, int warp,
-                                              int lane, int b0, int t0, int n0, const float* __restrict__ bias,
-                                              const float* __restrict__ residual, float* __restrict__ out,
-                                              float* __restrict__ out_relu) {
+// ===== epilogue: TMEM -> registers -> shared-memory transpose -> global =====
+// tcgen05.ld 32x32b hands lane l row l of the warp's 32-row TMEM quarter.  Stored straight from there every float4
+// access of a warp touches 32 different 128-byte lines, and the LSU spends one tag cycle per line: for the 1x1
+// convolutions of the residual blocks (read residual, write raw + ReLU'd copy: 12 KiB per 32-column chunk and warp)
+// that alone was 26 us of a 52 us kernel (ncu: 32 sectors per request, l1tex 48 % busy, lg_throttle stalls, tensor
+// pipe 18 %).  So each 32 x 32 chunk goes through a padded shared-memory tile and leaves transposed: 8 lanes cover
+// one row's 128 bytes, a warp instruction covers four full lines (8x fewer tag cycles), the residual is read the
+// same way, and it is fetched one chunk AHEAD so that its latency sits under the stores of the current chunk.
+// The tile's column chunks are dealt round-robin to `n_groups` groups of four warps.
+constexpr int STG_LD = 33;                       // floats per staged row: conflict-free both ways
+constexpr int STG_FLOATS_PER_WARP = 32 * STG_LD;
+__device__ __forceinline__ void conv_epilogue(const TcParams& p, uint32_t acc_tmem, uint64_t* accum_full,
+                                              uint32_t parity, float* __restrict__ stg, int group, int n_groups,
+                                              int warp, int lane, int b0, int t0, int n0,
+                                              const float* __restrict__ bias, const float* __restrict__ residual,
+                                              float* __restrict__ out, float* __restrict__ out_relu) {
   const int q = warp & 3;                       // TMEM lane quarter this warp may access
-  const int r = q * 32 + lane;                  // row of the tile
+  const bool vec = (p.out_ld & 3) == 0 && (p.out_chan_off & 3) == 0;
+  const int step = 32 * n_groups;
+  const int c4 = (lane & 7) * 4;
+  // transposed pass: this lane handles columns c4..c4+3 of rows i * 4 + (lane >> 3), i = 0..7
+  size_t trow_base[8];
+  unsigned tok = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int r = q * 32 + i * 4 + (lane >> 3);
+    const int b_local = r / p.Tbox, t_local = r - b_local * p.Tbox;
+    const bool ok = r < p.Bbox * p.Tbox && (b0 + b_local) < p.B && (t0 + t_local) < p.n_out;
+    tok |= ok ? (1u << i) : 0u;
+    trow_base[i] = ((size_t)(b0 + b_local) * p.out_rows_per_item + (t0 + t_local)) * (size_t)p.out_ld + p.out_chan_off;
+  }
+  // the row this lane reads from TMEM (the scalar path for ragged channel counts stores it directly)
+  const int r = q * 32 + lane;
   const int b_local = r / p.Tbox, t_local = r - b_local * p.Tbox;
   const bool row_ok = r < p.Bbox * p.Tbox && (b0 + b_local) < p.B && (t0 + t_local) < p.n_out;
   const size_t row_base = ((size_t)(b0 + b_local) * p.out_rows_per_item + (t0 + t_local)) * (size_t)p.out_ld +
                           p.out_chan_off;
-  const bool vec = (p.out_ld & 3) == 0 && (p.out_chan_off & 3) == 0;
-  mbar_wait(accum_full, 0);
+  float4 rr[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) rr[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  auto fetch_residual = [&](int cc) {
+    const int ncol = n0 + cc;
+    if (residual && cc < p.BN && vec && ncol + 32 <= p.C_out) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if ((tok >> i) & 1u) rr[i] = *reinterpret_cast<const float4*>(residual + trow_base[i] + ncol + c4);
+    }
+  };
+  fetch_residual(32 * group);                   // independent of the accumulator: issued before the wait
+  mbar_wait(accum_full, parity);
   tc_fence_after();
-  for (int cc = 0; cc < p.BN; cc += 32) {
+  for (int cc = 32 * group; cc < p.BN; cc += step) {
     uint32_t v[32];
-    __syncwarp();
-    tmem_ld_x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
-    if (!row_ok) continue;
+    __syncwarp();                               // the previous chunk has left the staging tile
+    tmem_ld_x32(acc_tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)cc, v);
     const int ncol = n0 + cc;                   // first output channel of this chunk
     if (vec && ncol + 32 <= p.C_out) {
 #pragma unroll
-      for (int j = 0; j < 32; j += 4) {
-        float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                               __uint_as_float(v[j + 3]));
-        if (bias) {
-          const float4 bb = *reinterpret_cast<const float4*>(bias + ncol + j);
-          o.x += bb.x; o.y += bb.y; o.z += bb.z; o.w += bb.w;
+      for (int j = 0; j < 32; ++j) stg[lane * STG_LD + j] = __uint_as_float(v[j]);
+      __syncwarp();
+      float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (bias) bb = *reinterpret_cast<const float4*>(bias + ncol + c4);
+      float4 o[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float* sr = stg + (i * 4 + (lane >> 3)) * STG_LD + c4;
+        o[i] = make_float4(sr[0] + bb.x + rr[i].x, sr[1] + bb.y + rr[i].y, sr[2] + bb.z + rr[i].z,
+                           sr[3] + bb.w + rr[i].w);
+      }
+      fetch_residual(cc + step);                // next chunk's residual is in flight while this one is stored
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        if ((tok >> i) & 1u) {
+          const size_t at = trow_base[i] + ncol + c4;
+          if (out) *reinterpret_cast<float4*>(out + at) = o[i];
+          if (out_relu)
+            *reinterpret_cast<float4*>(out_relu + at) =
+                make_float4(fmaxf(o[i].x, 0.f), fmaxf(o[i].y, 0.f), fmaxf(o[i].z, 0.f), fmaxf(o[i].w, 0.f));
         }
-        if (residual) {
-          const float4 rr = *reinterpret_cast<const float4*>(residual + row_base + ncol + j);
-          o.x += rr.x; o.y += rr.y; o.z += rr.z; o.w += rr.w;
-        }
-        if (out) *reinterpret_cast<float4*>(out + row_base + ncol + j) = o;
-        if (out_relu)
-          *reinterpret_cast<float4*>(out_relu + row_base + ncol + j) =
-              make_float4(fmaxf(o.x, 0.f), fmaxf(o.y, 0.f), fmaxf(o.z, 0.f), fmaxf(o.w, 0.f));
       }
     } else {
+      if (row_ok) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = ncol + j;
-        if (n < p.C_out) {
-          float o = __uint_as_float(v[j]);
-          if (bias) o += bias[n];
-          if (residual) o += residual[row_base + n];
-          if (out) out[row_base + n] = o;
-          if (out_relu) out_relu[row_base + n] = fmaxf(o, 0.f);
+        for (int j = 0; j < 32; ++j) {
+          const int n = ncol + j;
+          if (n < p.C_out) {
+            float o = __uint_as_float(v[j]);
+            if (bias) o += bias[n];
+            if (residual) o += residual[row_base + n];
+            if (out) out[row_base + n] = o;
+            if (out_relu) out_relu[row_base + n] = fmaxf(o, 0.f);
+          }
         }
       }
+      fetch_residual(cc + step);
     }
   }
 }
 
 // ---- kernel -----------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 1)
+// Persistent: CTA c takes tiles c, c + gridDim.x, ... (n fastest, so CTAs working at the same time share the
+// activation rows in L2).  Two TMEM accumulators: the epilogue of tile i (TMEM -> +bias, +residual -> global, the
+// memory-bound half of a 1x1 convolution) runs under the MMAs of tile i + 1; the TMA ring keeps running across tiles.
+__global__ void __launch_bounds__(384, 1)
     conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcParams p,
-                   const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ out,
-                   float* __restrict__ out_relu) {
+                   int tiles_n, int n_tiles, const float* __restrict__ bias, const float* __restrict__ residual,
+                   float* __restrict__ out, float* __restrict__ out_relu) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* smem_a = smem;                                  // [STAGES][16 KiB]
   unsigned char* smem_b = smem + STAGES * A_BYTES;               // [STAGES][32 KiB]
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
   uint64_t* empty = full + STAGES;
-  uint64_t* accum_full = empty + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = empty + STAGES;                           // [2]
+  uint64_t* acc_empty = acc_full + 2;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* staging = reinterpret_cast<float*>(tmem_slot + 4);      // [8 warps][32][STG_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
-  const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
-  const int b0 = tb * p.Bbox, t0 = tt * p.Tbox;
   const int n_iter = p.n_taps * p.kblocks;
-  const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : p.BN <= 128 ? 128 : 256;
+  const uint32_t tmem_cols = 2 * acc_cols;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -177,7 +228,10 @@ __global__ void __launch_bounds__(256, 1)
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 8);           // one arrive per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -196,13 +250,18 @@ __global__ void __launch_bounds__(256, 1)
     if (lane == 0) {
       const uint32_t a_bytes = (uint32_t)p.Bbox * p.Tbox * 128u, b_bytes = (uint32_t)p.BN * 128u;
       int it = 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int s = it % STAGES;
-          if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
-          tma_load_3d(smem_a + s * A_BYTES, &map_a, &full[s], p.chan_off[tap] + kb * BK, t0 + p.row_off[tap], b0);
-          tma_load_2d(smem_b + s * B_BYTES, &map_b, &full[s], kb * BK, tap * p.N_pad + n0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, n0 = (tile - tile_m * tiles_n) * p.BN;
+        const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
+        const int b0 = tb * p.Bbox, t0 = tt * p.Tbox;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const int s = it % STAGES;
+            if (it >= STAGES) mbar_wait(&empty[s], ((it / STAGES) - 1) & 1);
+            mbar_arrive_expect_tx(&full[s], a_bytes + b_bytes);
+            tma_load_3d(smem_a + s * A_BYTES, &map_a, &full[s], p.chan_off[tap] + kb * BK, t0 + p.row_off[tap], b0);
+            tma_load_2d(smem_b + s * B_BYTES, &map_b, &full[s], kb * BK, tap * p.N_pad + n0);
+          }
         }
       }
     }
@@ -212,23 +271,43 @@ __global__ void __launch_bounds__(256, 1)
       // instruction descriptor: D = F32, A = B = TF32, both K-major, N >> 3 at bit 17, M >> 4 at bit 24
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % STAGES;
-        mbar_wait(&full[s], (it / STAGES) & 1);
-        tc_fence_after();
-        const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * A_BYTES));
-        const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * B_BYTES));
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-          tc_mma_tf32(tmem_base, a_desc + 2u * k, b_desc + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        if (lt >= 2) {                         // the epilogue of the tile two back has drained this accumulator
+          mbar_wait(&acc_empty[as], ((lt >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        tc_commit(&empty[s]);      // arrives when the MMAs above have finished reading this stage
+        const uint32_t acc = tmem_base + (uint32_t)as * acc_cols;
+        for (int i = 0; i < n_iter; ++i, ++it) {
+          const int s = it % STAGES;
+          mbar_wait(&full[s], (it / STAGES) & 1);
+          tc_fence_after();
+          const uint64_t a_desc = umma_desc_sw128(smem_u32(smem_a + s * A_BYTES));
+          const uint64_t b_desc = umma_desc_sw128(smem_u32(smem_b + s * B_BYTES));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle row: +2 in the (addr >> 4) field
+            tc_mma_tf32(acc, a_desc + 2u * k, b_desc + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[s]);      // arrives when the MMAs above have finished reading this stage
+        }
+        tc_commit(&acc_full[as]);    // accumulator complete
       }
-      tc_commit(accum_full);       // accumulator complete
     }
   } else if (warp >= 4) {
-    conv_epilogue(p, tmem_base, accum_full, warp, lane, b0, t0, n0, bias, residual, out, out_relu);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile / tiles_n, n0 = (tile - tile_m * tiles_n) * p.BN;
+      const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
+      const int as = lt & 1;
+      conv_epilogue(p, tmem_base + (uint32_t)as * acc_cols, &acc_full[as], (uint32_t)((lt >> 1) & 1),
+                    staging + (warp - 4) * STG_FLOATS_PER_WARP, (warp - 4) >> 2, 2, warp, lane, tb * p.Bbox, tt * p.Tbox,
+                    n0, bias, residual, out, out_relu);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+    }
   }
 
   tc_fence_before();
@@ -253,21 +332,22 @@ constexpr int SPLIT_STAGE_BYTES = 4 * A_BYTES;
 
 __global__ void __launch_bounds__(384, 1)
     conv_tc3_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
-                    const __grid_constant__ CUtensorMap map_b_lo, TcParams p, const float* __restrict__ bias,
-                    const float* __restrict__ residual, float* __restrict__ out, float* __restrict__ out_relu) {
+                    const __grid_constant__ CUtensorMap map_b_lo, TcParams p, int tiles_n, int n_tiles,
+                    const float* __restrict__ bias, const float* __restrict__ residual, float* __restrict__ out,
+                    float* __restrict__ out_relu) {
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + SPLIT_STAGES * SPLIT_STAGE_BYTES);
   uint64_t* empty = full + SPLIT_STAGES;
   uint64_t* split = empty + SPLIT_STAGES;
-  uint64_t* accum_full = split + SPLIT_STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  uint64_t* acc_full = split + SPLIT_STAGES;                     // [2]
+  uint64_t* acc_empty = acc_full + 2;                            // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* staging = reinterpret_cast<float*>(tmem_slot + 2);      // [4 warps][32][STG_LD]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile_m = blockIdx.x, n0 = blockIdx.y * p.BN;
-  const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
-  const int b0 = tb * p.Bbox, t0 = tt * p.Tbox;
   const int n_iter = p.n_taps * p.kblocks;
-  const uint32_t tmem_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;
+  const uint32_t acc_cols = p.BN <= 32 ? 32 : p.BN <= 64 ? 64 : 128;
+  const uint32_t tmem_cols = 2 * acc_cols;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -280,7 +360,10 @@ __global__ void __launch_bounds__(384, 1)
       mbar_init(&empty[s], 1);
       mbar_init(&split[s], 4);              // one arrive per splitter warp
     }
-    mbar_init(accum_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&acc_full[s], 1);
+      mbar_init(&acc_empty[s], 4);          // one arrive per epilogue warp
+    }
     fence_mbar_init();
   }
   if (warp == 2) {
@@ -294,19 +377,26 @@ __global__ void __launch_bounds__(384, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
+  // persistent like conv_tc_kernel: tiles blockIdx.x, + gridDim.x, ...; the epilogue of one tile runs under the
+  // (three times longer) main loop of the next
   if (warp == 0) {
     if (lane == 0) {                                       // ===== TMA producer =====
       const uint32_t a_bytes = (uint32_t)p.Bbox * p.Tbox * 128u, b_bytes = (uint32_t)p.BN * 128u;
       int it = 0;
-      for (int tap = 0; tap < p.n_taps; ++tap) {
-        for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
-          const int s = it % SPLIT_STAGES;
-          if (it >= SPLIT_STAGES) mbar_wait(&empty[s], ((it / SPLIT_STAGES) - 1) & 1);
-          unsigned char* st = smem + s * SPLIT_STAGE_BYTES;
-          mbar_arrive_expect_tx(&full[s], a_bytes + 2 * b_bytes);
-          tma_load_3d(st, &map_a, &full[s], p.chan_off[tap] + kb * BK, t0 + p.row_off[tap], b0);
-          tma_load_2d(st + 2 * A_BYTES, &map_b, &full[s], kb * BK, tap * p.N_pad + n0);
-          tma_load_2d(st + 3 * A_BYTES, &map_b_lo, &full[s], kb * BK, tap * p.N_pad + n0);
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int tile_m = tile / tiles_n, n0 = (tile - tile_m * tiles_n) * p.BN;
+        const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
+        const int b0 = tb * p.Bbox, t0 = tt * p.Tbox;
+        for (int tap = 0; tap < p.n_taps; ++tap) {
+          for (int kb = 0; kb < p.kblocks; ++kb, ++it) {
+            const int s = it % SPLIT_STAGES;
+            if (it >= SPLIT_STAGES) mbar_wait(&empty[s], ((it / SPLIT_STAGES) - 1) & 1);
+            unsigned char* st = smem + s * SPLIT_STAGE_BYTES;
+            mbar_arrive_expect_tx(&full[s], a_bytes + 2 * b_bytes);
+            tma_load_3d(st, &map_a, &full[s], p.chan_off[tap] + kb * BK, t0 + p.row_off[tap], b0);
+            tma_load_2d(st + 2 * A_BYTES, &map_b, &full[s], kb * BK, tap * p.N_pad + n0);
+            tma_load_2d(st + 3 * A_BYTES, &map_b_lo, &full[s], kb * BK, tap * p.N_pad + n0);
+          }
         }
       }
     }
@@ -314,27 +404,39 @@ __global__ void __launch_bounds__(384, 1)
     if (lane == 0) {                                       // ===== MMA issuer =====
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int it = 0; it < n_iter; ++it) {
-        const int s = it % SPLIT_STAGES;
-        mbar_wait(&split[s], (it / SPLIT_STAGES) & 1);      // TMA landed AND the activation tile is split
-        tc_fence_after();
-        const uint32_t st = smem_u32(smem + s * SPLIT_STAGE_BYTES);
-        const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + A_BYTES);
-        const uint64_t b_hi = umma_desc_sw128(st + 2 * A_BYTES), b_lo = umma_desc_sw128(st + 3 * A_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          tc_mma_tf32(tmem_base, a_lo + 2u * k, b_hi + 2u * k, idesc, (it | k) != 0 ? 1u : 0u);   // small terms first
-          tc_mma_tf32(tmem_base, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
-          tc_mma_tf32(tmem_base, a_hi + 2u * k, b_hi + 2u * k, idesc, 1u);
+      int it = 0, lt = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+        const int as = lt & 1;
+        if (lt >= 2) {
+          mbar_wait(&acc_empty[as], ((lt >> 1) - 1) & 1);
+          tc_fence_after();
         }
-        tc_commit(&empty[s]);
+        const uint32_t acc = tmem_base + (uint32_t)as * acc_cols;
+        for (int i = 0; i < n_iter; ++i, ++it) {
+          const int s = it % SPLIT_STAGES;
+          mbar_wait(&split[s], (it / SPLIT_STAGES) & 1);    // TMA landed AND the activation tile is split
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + s * SPLIT_STAGE_BYTES);
+          const uint64_t a_hi = umma_desc_sw128(st), a_lo = umma_desc_sw128(st + A_BYTES);
+          const uint64_t b_hi = umma_desc_sw128(st + 2 * A_BYTES), b_lo = umma_desc_sw128(st + 3 * A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            tc_mma_tf32(acc, a_lo + 2u * k, b_hi + 2u * k, idesc, (i | k) != 0 ? 1u : 0u);   // small terms first
+            tc_mma_tf32(acc, a_hi + 2u * k, b_lo + 2u * k, idesc, 1u);
+            tc_mma_tf32(acc, a_hi + 2u * k, b_hi + 2u * k, idesc, 1u);
+          }
+          tc_commit(&empty[s]);
+        }
+        tc_commit(&acc_full[as]);
       }
-      tc_commit(accum_full);
     }
   } else if (warp >= 8) {
     // ===== splitter: A -> (A_hi in place, A_lo) for the whole 16 KiB tile; elementwise, so the swizzle is irrelevant
     const int t = threadIdx.x - 256;                       // 0..127
-    for (int it = 0; it < n_iter; ++it) {
+    int n_local = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) ++n_local;
+    const int total = n_local * n_iter;
+    for (int it = 0; it < total; ++it) {
       const int s = it % SPLIT_STAGES;
       mbar_wait(&full[s], (it / SPLIT_STAGES) & 1);
       float4* a = reinterpret_cast<float4*>(smem + s * SPLIT_STAGE_BYTES);
@@ -358,7 +460,18 @@ __global__ void __launch_bounds__(384, 1)
       }
     }
   } else if (warp >= 4) {
-    conv_epilogue(p, tmem_base, accum_full, warp, lane, b0, t0, n0, bias, residual, out, out_relu);
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++lt) {
+      const int tile_m = tile / tiles_n, n0 = (tile - tile_m * tiles_n) * p.BN;
+      const int tb = tile_m / p.tiles_t, tt = tile_m - tb * p.tiles_t;
+      const int as = lt & 1;
+      conv_epilogue(p, tmem_base + (uint32_t)as * acc_cols, &acc_full[as], (uint32_t)((lt >> 1) & 1),
+                    staging + (warp - 4) * STG_FLOATS_PER_WARP, 0, 1, warp, lane, tb * p.Bbox, tt * p.Tbox, n0, bias,
+                    residual, out, out_relu);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&acc_empty[as])) : "memory");
+    }
   }
 
   tc_fence_before();
@@ -455,16 +568,21 @@ static int conv_tc_launch(const qpg_conv_tc_desc_t* d, const float* in, const fl
     }
   }
   const int tiles_b = (d->B + p.Bbox - 1) / p.Bbox;
-  dim3 grid((unsigned)(tiles_b * p.tiles_t), (unsigned)(d->N_pad / d->BN));
+  const int tiles_n = d->N_pad / d->BN, n_tiles = tiles_b * p.tiles_t * tiles_n;
+  const int ctas = n_tiles < sm_count() ? n_tiles : sm_count();          // persistent CTAs, round-robin over the tiles
   // the shared-memory attribute is per device: set it on every launch (a process may use several GPUs)
   if (split) {
-    const size_t smem = (size_t)SPLIT_STAGES * SPLIT_STAGE_BYTES + (3 * SPLIT_STAGES + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)SPLIT_STAGES * SPLIT_STAGE_BYTES + (3 * SPLIT_STAGES + 4) * sizeof(uint64_t) + 16 +
+                        4 * STG_FLOATS_PER_WARP * sizeof(float);
     QPG_CUDA(cudaFuncSetAttribute(conv_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc3_kernel<<<grid, 384, smem, (cudaStream_t)stream>>>(map_a, map_b, map_b_lo, p, bias, residual, out, out_relu);
+    conv_tc3_kernel<<<ctas, 384, smem, (cudaStream_t)stream>>>(map_a, map_b, map_b_lo, p, tiles_n, n_tiles, bias, residual,
+                                                              out, out_relu);
   } else {
-    const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+    const size_t smem = (size_t)STAGES * (A_BYTES + B_BYTES) + (2 * STAGES + 4) * sizeof(uint64_t) + 16 +
+                        8 * STG_FLOATS_PER_WARP * sizeof(float);
     QPG_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(map_a, map_b, p, bias, residual, out, out_relu);
+    conv_tc_kernel<<<ctas, 384, smem, (cudaStream_t)stream>>>(map_a, map_b, p, tiles_n, n_tiles, bias, residual, out,
+                                                             out_relu);
   }
   QPG_LAUNCH_CHECK();
   return QPG_OK;
