@@ -164,7 +164,25 @@ pae_params_kernel(const float* __restrict__ latent, const float* __restrict__ fc
     __syncthreads();
     const int e = e0 + warp;
     if (e >= E) continue;
-    const double* y = ys[warp];
+    double* y = ys[warp];
+    // offset and the two Linear(T, 2) outputs first; then the row is centred in place, so that the DFT below sees
+    // y - mean (same bins k >= 1 mathematically, no large DC part in the sums, and an exactly constant latent gives
+    // an exactly zero spectrum -> 0 / 0 = NaN frequency, the value of PAE.py:106 for zero power)
+    double s_y = 0.0, v0 = 0.0, v1 = 0.0;
+    for (int t = lane; t < T; t += 32) {
+      s_y += y[t];
+      v0 = fma((double)fcw[((size_t)e * 2 + 0) * T + t], y[t], v0);
+      v1 = fma((double)fcw[((size_t)e * 2 + 1) * T + t], y[t], v1);
+    }
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      s_y += __shfl_xor_sync(0xffffffffu, s_y, off);
+      v0 += __shfl_xor_sync(0xffffffffu, v0, off);
+      v1 += __shfl_xor_sync(0xffffffffu, v1, off);
+    }
+    const double mean = s_y / T;
+    for (int t = lane; t < T; t += 32) y[t] -= mean;
+    __syncwarp();
     // power spectrum without the DC bin, bins spread over the lanes
     double s_pow = 0.0, s_fpow = 0.0;
     for (int kb = 1 + lane; kb <= T / 2; kb += 32) {
@@ -180,19 +198,10 @@ pae_params_kernel(const float* __restrict__ latent, const float* __restrict__ fc
       s_pow += pw;
       s_fpow = fma((double)freqs[kb - 1], pw, s_fpow);
     }
-    double s_y = 0.0, v0 = 0.0, v1 = 0.0;
-    for (int t = lane; t < T; t += 32) {
-      s_y += y[t];
-      v0 = fma((double)fcw[((size_t)e * 2 + 0) * T + t], y[t], v0);
-      v1 = fma((double)fcw[((size_t)e * 2 + 1) * T + t], y[t], v1);
-    }
 #pragma unroll
     for (int off = 16; off; off >>= 1) {
       s_pow += __shfl_xor_sync(0xffffffffu, s_pow, off);
       s_fpow += __shfl_xor_sync(0xffffffffu, s_fpow, off);
-      s_y += __shfl_xor_sync(0xffffffffu, s_y, off);
-      v0 += __shfl_xor_sync(0xffffffffu, v0, off);
-      v1 += __shfl_xor_sync(0xffffffffu, v1, off);
     }
     if (lane == 0) {
       const double vx = (double)fc_scale[e * 2 + 0] * v0 + (double)fc_shift[e * 2 + 0];
@@ -206,7 +215,7 @@ pae_params_kernel(const float* __restrict__ latent, const float* __restrict__ fc
       out[0 * E + e] = (float)(ph / (2.0 * kPi));
       out[1 * E + e] = (float)(s_fpow / s_pow / (double)time_scale);       // 0 / 0 -> NaN, as in the reference
       out[2 * E + e] = (float)(2.0 * sqrt(s_pow) / T);
-      out[3 * E + e] = (float)(s_y / T);
+      out[3 * E + e] = (float)mean;
     }
   }
 }
