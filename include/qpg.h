@@ -394,6 +394,38 @@ int qpg_pae_conv1d(const float* x, const float* w, const float* scale, const flo
 int qpg_pae_params(const float* latent, const float* fcw, const float* fc_scale, const float* fc_shift,
                    const float* freqs, float time_scale, int B, int E, int T, float* params, void* stream);
 
+/* ---------------- legacy pose-feature matcher: the `GestureKNN` class (GestureKNN.py:70-284) ----------------
+ * One 8-frame step of `search_motion` (metric 0) or `search_fake_motion` (metric 1) for a BATCH of clips:
+ * qpg_legacy_candidates (frame candidates per database sequence + rank transforms), qpg_legacy_pick (desired_k-th of
+ * the rank-sum order; or the caller picks with np.argsort to reproduce NumPy's order among tied sums),
+ * qpg_legacy_gather.
+ *   feat   [n_seq, n_frames, F] float64 normalised features (audio part first, then the pose part), motion
+ *          [n_seq, n_frames, J] float64, mask [n_seq, n_frames] int32 (control mask).
+ *   query  [n_clips, q_ld]: metric 0 = pose feature of the previous frame (n_body values, L2, :169-171),
+ *          metric 1 = audio feature of the current frame (n_aud values, sklearn cosine, :258);
+ *   aud_query [n_clips, n_aud] (metric 0 only): audio feature of the current frame (:125-132).
+ *   desired_k [n_clips]; j0 = first output column of this step; pred [n_clips, J, out_frames] float64.
+ *   next_pose [n_clips, n_body] (nullable): pose feature of the last copied frame = the next step's query (:146).
+ *   chosen_log [n_clips, n_steps, 2] (nullable): (sequence, frame) picked at step_idx.
+ *   status [n_clips], caller-zeroed: bit 0 = fewer than desired_k + 1 candidates (IndexError at :144 in the
+ *          reference; the clip stops), bit 1 = an exact tie (NumPy's unstable argsort decides in the reference).
+ *   scratch: cands n_clips * n_seq * qpg_legacy_cand_bytes(), comb / tie_flag [n_clips, n_seq] int32, chosen
+ *          [n_clips, 2] int32, n_found [n_clips] int32.
+ */
+size_t qpg_legacy_cand_bytes(void);
+/* frame candidates per (clip, sequence) + rank sums: cands, comb [n_clips, n_seq] (-1 = no candidate), tie_flag */
+int qpg_legacy_candidates(const double* feat, const int32_t* mask, int n_seq, int n_frames, int F, int n_aud, int n_body,
+                          int step_sz, int n_clips, int metric, const double* query, int q_ld, const double* aud_query,
+                          void* cands, int32_t* comb, int32_t* tie_flag, void* stream);
+/* stable device pick: chosen [n_clips, 2] = (sequence, frame) at position desired_k of the order by (comb, sequence) */
+int qpg_legacy_pick(const void* cands, const int32_t* comb, const int32_t* tie_flag, int n_seq, int n_clips,
+                    const int32_t* desired_k, int32_t* chosen, int32_t* n_found, int32_t* status, void* stream);
+/* copy the chosen frames into pred, feed the pose feature back, log the choice; n_found <= desired_k -> status bit 0 */
+int qpg_legacy_gather(const double* feat, const double* motion, int n_seq, int n_frames, int F, int J, int n_aud,
+                      int n_body, int step_sz, int n_clips, const int32_t* chosen, const int32_t* n_found,
+                      const int32_t* desired_k, int j0, int out_frames, int step_idx, int n_steps, double* pred,
+                      double* next_pose, int32_t* chosen_log, int32_t* status, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -786,6 +786,142 @@ class CodeKNN(object):
 MAX_TABLE_WALK_CLIPS = 2
 
 
+class GestureKNN(object):
+    """The reference's legacy pose-feature matcher (GestureKNN.py:70-284) on the device: same constructor, `init_frame`,
+    `search_motion(feat_test, desired_k)` and `search_fake_motion(feat_test, desired_k)` with the reference's shapes
+    and return values, plus batched forms that advance many clips together (csrc/legacy_knn.cu: four launches per
+    8-frame step whatever the batch size).  `last_status` holds the per-clip status of the last call (bit 0: fewer
+    candidates than desired_k + 1, where the reference raises IndexError - raised here too; bit 1: the result
+    depended on the order of exact ties, which NumPy's unstable argsort decides in the reference)."""
+
+    def __init__(self, feat_train, motn_train, control_mask, n_aud_feat=112, n_body_feat=96, n_joints=165, step_sz=8,
+                 device=None, ties="numpy"):
+        """ties: "numpy" (default) - the one choice per step among the rank sums (small integers, often tied) is made
+        by np.argsort on the host, as in the reference (:139), at the cost of one small device->host copy per step;
+        "stable" - everything on the device, lower sequence first among tied sums, ties reported in last_status."""
+        if ties not in ("numpy", "stable"):
+            raise ValueError("ties must be 'numpy' or 'stable'")
+        self.ties = ties
+        self.n_aud_feat, self.n_body_feat, self.n_joints, self.step_sz = n_aud_feat, n_body_feat, n_joints, step_sz
+        self.feat_train, self.motn_train, self.control_mask = feat_train, motn_train, control_mask
+        self.n_db_seq, self.n_db_frm = feat_train.shape[0], feat_train.shape[1]
+        self.device = torch.device(device if device is not None else "cuda")
+        _lib.load()                                           # fail loudly without the CUDA library
+        if feat_train.shape[2] < n_aud_feat + n_body_feat or motn_train.shape[2] != n_joints:
+            raise ValueError("feature / motion widths do not match n_aud_feat + n_body_feat / n_joints")
+        self._feat = torch.as_tensor(np.ascontiguousarray(feat_train, dtype=np.float64), device=self.device)
+        self._motn = torch.as_tensor(np.ascontiguousarray(motn_train, dtype=np.float64), device=self.device)
+        self._mask = torch.as_tensor(np.ascontiguousarray(np.asarray(control_mask) != 0, dtype=np.int32), device=self.device)
+        self.last_status = None
+        self.last_chosen = None
+
+    def init_frame(self):
+        """GestureKNN.py:89-97: the same draws from NumPy's global generator."""
+        init_seq = np.random.randint(0, self.n_db_seq)
+        init_frm = np.random.randint(0, self.n_db_frm)
+        while self.control_mask[init_seq, init_frm] != 1:
+            init_seq = np.random.randint(0, self.n_db_seq)
+            init_frm = np.random.randint(0, self.n_db_frm)
+        return init_seq, init_frm
+
+    def _run(self, feat_tests, desired_k, inits, fake):
+        lib, dev = _lib.load(), self.device
+        ft = torch.as_tensor(np.ascontiguousarray(feat_tests, dtype=np.float64), device=dev)     # [B, n_aud(+), n_frames]
+        B, n_frames = ft.shape[0], ft.shape[2]
+        na, nb, J, st, S = self.n_aud_feat, self.n_body_feat, self.n_joints, self.step_sz, self.n_db_seq
+        aud = ft[:, :na, :].permute(0, 2, 1).contiguous()                                          # [B, n_frames, n_aud]
+        dk_host = np.broadcast_to(np.asarray(desired_k, dtype=np.int32), (B,)).copy()
+        dk = torch.as_tensor(dk_host, device=dev)
+        starts = list(range(0, n_frames, st)) if fake else list(range(1, n_frames, st))
+        out_frames = n_frames if fake else n_frames + 1
+        pred = torch.zeros((B, J, out_frames), dtype=torch.float64, device=dev)
+        cand_bytes = int(lib.qpg_legacy_cand_bytes())
+        cands = torch.empty((B, S, cand_bytes), dtype=torch.uint8, device=dev)
+        comb = torch.empty((B, S), dtype=torch.int32, device=dev)
+        tie = torch.empty_like(comb)
+        chosen = torch.zeros((B, 2), dtype=torch.int32, device=dev)
+        n_found = torch.zeros((B,), dtype=torch.int32, device=dev)
+        log = torch.full((B, len(starts), 2), -1, dtype=torch.int32, device=dev)
+        status = torch.zeros((B,), dtype=torch.int32, device=dev)
+        pose = None
+        if not fake:
+            idx = torch.as_tensor(np.asarray(inits, dtype=np.int64).reshape(B, 2), device=dev)
+            pose = self._feat[idx[:, 0], idx[:, 1], na:na + nb].contiguous()                     # :111
+        sp = _lib.stream_ptr()
+        F = self._feat.shape[2]
+        for s_i, j in enumerate(starts):
+            a_q = aud[:, j if fake else j - 1].contiguous()           # feat_test' column j = feat_test column j - 1 (:105)
+            query = a_q if fake else pose
+            _lib.check(lib.qpg_legacy_candidates(
+                _lib.ptr(self._feat), _lib.ptr(self._mask), S, self.n_db_frm, F, na, nb, st, B, 1 if fake else 0,
+                _lib.ptr(query), query.shape[1], None if fake else _lib.ptr(a_q), _lib.ptr(cands), _lib.ptr(comb),
+                _lib.ptr(tie), sp), "qpg_legacy_candidates")
+            if self.ties == "numpy":
+                # the reference's own call on the rank sums (GestureKNN.py:139): NumPy's order among tied sums
+                comb_h = comb.cpu().numpy()
+                frames_h = cands.cpu().numpy()[:, :, 16:20].copy().view(np.int32)[:, :, 0]
+                ch, nf = np.zeros((B, 2), dtype=np.int32), np.zeros((B,), dtype=np.int32)
+                for b in range(B):
+                    found = np.nonzero(comb_h[b] >= 0)[0]
+                    nf[b] = len(found)
+                    if dk_host[b] < len(found):
+                        w = found[np.argsort(comb_h[b][found].astype(np.int64))[dk_host[b]]]
+                        ch[b] = (w, frames_h[b, w])
+                chosen.copy_(torch.from_numpy(ch))
+                n_found.copy_(torch.from_numpy(nf))
+            else:
+                _lib.check(lib.qpg_legacy_pick(_lib.ptr(cands), _lib.ptr(comb), _lib.ptr(tie), S, B, _lib.ptr(dk),
+                                               _lib.ptr(chosen), _lib.ptr(n_found), _lib.ptr(status), sp), "qpg_legacy_pick")
+            _lib.check(lib.qpg_legacy_gather(
+                _lib.ptr(self._feat), _lib.ptr(self._motn), S, self.n_db_frm, F, J, na, nb, st, B, _lib.ptr(chosen),
+                _lib.ptr(n_found), _lib.ptr(dk), j, out_frames, s_i, len(starts), _lib.ptr(pred),
+                None if fake else _lib.ptr(pose), _lib.ptr(log), _lib.ptr(status), sp), "qpg_legacy_gather")
+        self.last_status = status.cpu().numpy()
+        self.last_chosen = log.cpu().numpy()
+        if (self.last_status & 1).any():
+            bad = int(np.nonzero(self.last_status & 1)[0][0])
+            raise IndexError(f"clip {bad}: fewer candidates than desired_k + 1 (GestureKNN.py:144)")
+        out = pred.cpu().numpy()
+        return out if fake else out[:, :, 1:]
+
+    def search_motion_batch(self, feat_tests, desired_k, inits=None):
+        """feat_tests [B, n_aud_feat, n_frames]; inits [B, 2] = (sequence, frame) per clip (default: init_frame()
+        per clip, in order).  Returns [B, n_joints, n_frames]."""
+        B = len(feat_tests)
+        if inits is None:
+            inits = [self.init_frame() for _ in range(B)]
+        return self._run(feat_tests, desired_k, inits, fake=False)
+
+    def search_fake_motion_batch(self, feat_tests, desired_k):
+        return self._run(feat_tests, desired_k, None, fake=True)
+
+    def search_motion(self, feat_test, desired_k):
+        """GestureKNN.py:100-152 -> pred_motion [n_joints, n_frames]."""
+        return self.search_motion_batch(np.asarray(feat_test)[None], desired_k)[0]
+
+    def search_fake_motion(self, feat_test, desired_k):
+        """GestureKNN.py:217-243 -> pred_motion [n_joints, n_frames]."""
+        return self.search_fake_motion_batch(np.asarray(feat_test)[None], desired_k)[0]
+
+
+def predict_gesture_from_audio(feat_train, pose_train, feat_test, control_mask, data_stats, k=0, n_aud_feat=112,
+                               n_body_feat=96, n_joints=165, step_sz=8, frames=0, fake=False, device=None):
+    """GestureKNN.py:287-341 (`fake` replaces the module-global args.fake): normalise, build the matcher, match every
+    test sequence - all of them in ONE batched call instead of a Python loop.  Returns [n_test, n_joints, n_frames]."""
+    feat_mean, feat_std = data_stats['feat_mean'], data_stats['feat_std']
+    norm = lambda d, m, sd: (d - m) / (sd + 1E-8)                                   # utils.normalize_data
+    norm_feat_test = norm(feat_test, feat_mean[:, :n_aud_feat], feat_std[:, :n_aud_feat])
+    norm_feat_train = norm(feat_train, feat_mean, feat_std).transpose((0, 2, 1))
+    n_test_seq = frames if frames != 0 else feat_test.shape[0]
+    knn = GestureKNN(feat_train=norm_feat_train, motn_train=pose_train.transpose((0, 2, 1)), control_mask=control_mask,
+                     n_aud_feat=n_aud_feat, n_body_feat=n_body_feat, n_joints=n_joints, step_sz=step_sz, device=device)
+    p = [0.5] + [0.5 / 14] * 14
+    desired_k = np.random.choice(15, n_test_seq, p=p)                               # :322-323 (drawn in both modes)
+    if fake:
+        return knn.search_fake_motion_batch(norm_feat_test[:n_test_seq], desired_k)
+    return knn.search_motion_batch(norm_feat_test[:n_test_seq], k)
+
+
 def _phase_ntc(phase_train):
     """CodeKNN receives phase as (N, 240, 4[, 8]); accept the (N, 4, 240[, 8]) layout
     load_db_codebook returns as well."""

@@ -70,5 +70,28 @@ def main():
     print(json.dumps(dict(kernel="table_merge_kernel", parts=8, Q=Q,
                           ms=timed(lambda: lib.qpg_table_merge(_lib.ptr(parts), 8, Q * 512, _lib.ptr(out), sp)))))
 
+def legacy():
+    """legacy pose-feature matcher (GestureKNN class): seconds per batch of 64-frame clips against a synthetic database"""
+    import time
+    from qpgesture_b200.GestureKNN import GestureKNN
+    rng = np.random.default_rng(0)
+    n_seq, n_frames, B = 2048, 64, 64
+    feat = rng.standard_normal((n_seq, n_frames, 208)); motn = rng.standard_normal((n_seq, n_frames, 165))
+    mask = np.ones((n_seq, n_frames), dtype=np.int64)
+    tests = rng.standard_normal((B, 112, n_frames))
+    inits = [(int(rng.integers(n_seq)), int(rng.integers(n_frames))) for _ in range(B)]
+    for ties in ("stable", "numpy"):
+        knn = GestureKNN(feat, motn, mask, device="cuda:0", ties=ties)
+        knn.search_motion_batch(tests, 0, inits)
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        knn.search_motion_batch(tests, 0, inits)
+        torch.cuda.synchronize(); dt = time.perf_counter() - t0
+        print(json.dumps(dict(kernel="legacy GestureKNN.search_motion_batch", ties=ties, n_seq=n_seq, n_frames=n_frames,
+                              clips=B, seconds_per_batch=dt, clips_per_s=B / dt,
+                              frame_distances_per_s=B * 8 * n_seq * n_frames / dt)), flush=True)
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "legacy":
+        legacy()
+    else:
+        main()
