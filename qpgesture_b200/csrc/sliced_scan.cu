@@ -561,129 +561,198 @@ struct TablePair {
 
 // One warp per (table, start code, group of BG queries): U = min hi over the bin's rows; candidates = rows whose
 // interval reaches below U.  One candidate -> record (lo, hi, id).  Several -> float64 re-evaluation of exactly
-// those rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  BG queries share one trip over the
-// bin's rows (row_info is loaded once, the BG sacc loads are independent: the kernel is latency bound).  With
-// `consume` the entries of sacc are zeroed once read, so the next pass needs no memset.
-constexpr int BG = 4;
-__global__ void __launch_bounds__(256, 2)
-    sliced_bins_kernel(const TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset, int64_t row_base,
-                       int consume, unsigned long long* __restrict__ stats) {
-  const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
-  const int lane = threadIdx.x & 31;
-  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
-  const int n_groups = (nq + BG - 1) / BG;
-  if (wid >= (long long)n_groups * KB) return;
-  const int q0 = (int)(wid / KB) * BG, c = (int)(wid % KB);
-  const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
-  QConst qi[BG];
-#pragma unroll
-  for (int g = 0; g < BG; ++g) qi[g] = make_qconst(T.q_info[min(q0 + g, nq - 1)]);
-  double U[BG], lo0[BG], hi0[BG];
-#pragma unroll
-  for (int g = 0; g < BG; ++g) {
-    U[g] = 1e300;
-    lo0[g] = hi0[g] = 0.0;
-  }
-  // pass 1: U per query; the intervals of the first 32 rows (most bins have no more) stay in registers
-  for (int pos = b0 + lane; pos < b1; pos += 32) {
-    const RowInfo ri = T.row_info[pos];
-    long long v[BG];
-#pragma unroll
-    for (int g = 0; g < BG; ++g) v[g] = T.sacc[(size_t)min(q0 + g, nq - 1) * Wpad + pos];
-#pragma unroll
-    for (int g = 0; g < BG; ++g) {
-      const Interval iv = filter_interval(v[g], ri, qi[g]);
-      if (pos < b0 + 32) {
-        lo0[g] = iv.lo;
-        hi0[g] = iv.hi;
-      }
-      U[g] = fmin(U[g], iv.hi);
+// those rows (lexicographic (d, id) minimum) -> exact record lo = hi = d.  With `consume` the entries of sacc are
+// zeroed once read, so the next pass needs no memset.
+//
+// The kernel is latency bound (three dependent round trips: bin bounds -> rows -> record), so it is organised for
+// work per round trip and residency: the BG = 8 sacc loads of a lane are issued together, a bin of up to 32 rows
+// (nearly all of them at 26 windows per sequence) is settled from registers in ONE trip over its rows, the
+// per-query constants sit in shared memory, and the 64-bit minimum over the warp is two REDUX instead of ten
+// shuffles - 56 registers, four CTAs per SM (the first version: four queries, two trips, 128 registers, 28.8 us).
+constexpr int BG = 8;
+
+__device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
+  const unsigned hi = (unsigned)(v >> 32);
+  const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+  const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? (unsigned)v : 0xffffffffu);
+  return ((unsigned long long)mh << 32) | ml;
+}
+
+// several candidates in one bin: exact distances of exactly those rows; `m` = ballot of the candidate lanes of the
+// 32 rows starting at `base`.  Updates the running lexicographic (d, id) minimum.
+struct BestPair {
+  double d;
+  long long id;
+};
+__device__ __noinline__ BestPair bins_verify(const float* __restrict__ packed, const double* __restrict__ sqnorm,
+                                             const int32_t* __restrict__ order, int NC, int D, unsigned m, int base,
+                                             const float* qrow, double sqq, int64_t id_offset, int64_t row_base,
+                                             int lane, BestPair best) {
+  while (m) {
+    const int src_lane = __ffs(m) - 1;
+    m &= m - 1;
+    const long long w = order[base + src_lane];
+    const double d = exact_distance(packed, NC, w + row_base, qrow, D, sqq, sqnorm[w + row_base], lane);
+    const long long id = id_offset + w;
+    if (d < best.d || (d == best.d && id < best.id)) {
+      best.d = d;
+      best.id = id;
     }
   }
-#pragma unroll
-  for (int g = 0; g < BG; ++g)
-#pragma unroll
-    for (int o = 16; o >= 1; o >>= 1) U[g] = fmin(U[g], __shfl_xor_sync(0xffffffffu, U[g], o));
+  return best;
+}
 
+// T refers to kernel-parameter space with a STATIC index (see the kernel below): its fields are read from the
+// constant bank where they are used instead of occupying ~26 registers for the whole kernel
+__device__ __forceinline__ void bins_body(const TableParams& T, QConst* s_qc, long long* s_v, long long W, long long Wpad, int nq,
+                                          int64_t id_offset, int64_t row_base, int consume,
+                                          unsigned long long* __restrict__ stats) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int q0 = blockIdx.y * BG, c = blockIdx.x * 8 + warp;
+  if (threadIdx.x < BG) s_qc[threadIdx.x] = make_qconst(T.q_info[min(q0 + (int)threadIdx.x, nq - 1)]);
+  const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
+  __syncthreads();
+  const int n = b1 - b0;
+  const int ng = min(BG, nq - q0);
+  const unsigned long long kInf = ~0ull;
+  if (n <= 32) {
+    // ---- the whole bin in one trip: lane = row.  The BG accumulators of a row go global -> shared by cp.async
+    // (eight copies in flight per lane without holding 16 registers), then one query at a time ----
+    const bool valid = lane < n;
+    const int pos = b0 + lane;
+    RowInfo ri;
+    ri.r1 = ri.r2 = 0.0;
+    long long* my_v = s_v + (warp * BG) * 32 + lane;
+    if (valid) {
+#pragma unroll
+      for (int g = 0; g < BG; ++g) {
+        const long long* src = T.sacc + (size_t)min(q0 + g, nq - 1) * Wpad + pos;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(my_v + g * 32)), "l"(src) : "memory");
+      }
+      ri = T.row_info[pos];
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
 #pragma unroll 1
-  for (int g = 0; g < BG; ++g) {
-    const int qi_ = q0 + g;
-    if (qi_ >= nq) break;
-    long long* sv = T.sacc + (size_t)qi_ * Wpad;
-    const float* qrow = T.q + (size_t)qi_ * T.ldq;
-    const QConst qg = g == 0 ? qi[0] : g == 1 ? qi[1] : g == 2 ? qi[2] : qi[3];
-    const double sqq = T.q_info[qi_].sq;
-    const double Ug = g == 0 ? U[0] : g == 1 ? U[1] : g == 2 ? U[2] : U[3];
-    const double l0 = g == 0 ? lo0[0] : g == 1 ? lo0[1] : g == 2 ? lo0[2] : lo0[3];
-    qpg_bin_t rec;
-    rec.lo = kEmptyDist;
-    rec.hi = kEmptyDist;
-    rec.id = -1;
-    rec.n = 0;
-    rec.flags = 1;                               // empty bins are exact (sentinel)
-    if (b1 > b0) {
-      int n = 0;
-      double best_lo = 1e300, best_d = 1e300;
-      long long best_id = -1, single_pos = -1;
+    for (int g = 0; g < ng; ++g) {
+      const int qi_ = q0 + g;
+      qpg_bin_t rec;
+      rec.lo = kEmptyDist;
+      rec.hi = kEmptyDist;
+      rec.id = -1;
+      rec.n = 0;
+      rec.flags = 1;                             // empty bins are exact (sentinel)
+      if (n > 0) {
+        Interval iv;
+        iv.lo = iv.hi = 0.0;
+        if (valid) {
+          iv = filter_interval(my_v[g * 32], ri, s_qc[g]);
+          if (consume) T.sacc[(size_t)qi_ * Wpad + pos] = 0;
+        }
+        // non-negative doubles order like their bit patterns
+        const unsigned long long U = warp_min_u64(valid ? (unsigned long long)__double_as_longlong(iv.hi) : kInf);
+        const bool cand = valid && (unsigned long long)__double_as_longlong(iv.lo) <= U;
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        if (__popc(m) == 1) {
+          const int src = __ffs(m) - 1;
+          rec.lo = __shfl_sync(0xffffffffu, iv.lo, src);
+          rec.hi = __longlong_as_double((long long)U);
+          rec.id = id_offset + T.order[b0 + src];
+          rec.n = 1;
+          rec.flags = 0;
+        } else {
+          BestPair best;
+          best.d = 1e300;
+          best.id = -1;
+          best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m, b0, T.q + (size_t)qi_ * T.ldq, T.q_info[qi_].sq,
+                             id_offset, row_base, lane, best);
+          rec.lo = best.d;
+          rec.hi = best.d;
+          rec.id = best.id;
+          rec.n = __popc(m);                     // how many rows were re-evaluated (diagnostics)
+          rec.flags = 1;                         // exact
+          if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)rec.n);
+        }
+      }
+      if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
+    }
+  } else {
+    // ---- long bins (all-speaker tables: ~1700 rows per code): two trips per query, 32 rows at a time ----
+#pragma unroll 1
+    for (int g = 0; g < ng; ++g) {
+      const int qi_ = q0 + g;
+      long long* sv = T.sacc + (size_t)qi_ * Wpad;
+      const QConst qg = s_qc[g];
+      unsigned long long Ul = kInf;
+      for (int pos = b0 + lane; pos < b1; pos += 32)
+        Ul = min(Ul, (unsigned long long)__double_as_longlong(filter_interval(sv[pos], T.row_info[pos], qg).hi));
+      const unsigned long long U = warp_min_u64(Ul);
+      int cnt = 0;
+      double best_lo = 0.0;
+      BestPair best;
+      best.d = 1e300;
+      best.id = -1;
+      long long single_pos = -1;
+      const float* qrow = T.q + (size_t)qi_ * T.ldq;
+      const double sqq = T.q_info[qi_].sq;
       for (int base = b0; base < b1; base += 32) {
         const int pos = base + lane;
         bool cand = false;
         double lo = 0.0;
         if (pos < b1) {
-          lo = base == b0 ? l0 : filter_interval(sv[pos], T.row_info[pos], qg).lo;
-          cand = lo <= Ug;
+          lo = filter_interval(sv[pos], T.row_info[pos], qg).lo;
+          cand = (unsigned long long)__double_as_longlong(lo) <= U;
           if (consume) sv[pos] = 0;
         }
         const unsigned m = __ballot_sync(0xffffffffu, cand);
-        const int cnt = __popc(m);
-        if (cnt == 0) continue;
-        if (n == 0 && cnt == 1) {          // remember the first lone candidate; verified only if another shows up
-          const int src_lane = __ffs(m) - 1;
-          single_pos = base + src_lane;
-          best_lo = __shfl_sync(0xffffffffu, lo, src_lane);
-          n = 1;
+        const int k = __popc(m);
+        if (k == 0) continue;
+        if (cnt == 0 && k == 1) {                // remember the first lone candidate; verified only if another shows up
+          const int src = __ffs(m) - 1;
+          single_pos = base + src;
+          best_lo = __shfl_sync(0xffffffffu, lo, src);
+          cnt = 1;
           continue;
         }
-        // more than one candidate so far: evaluate exactly (including the remembered one)
-        if (n == 1 && single_pos >= 0) {
+        if (single_pos >= 0) {                   // a second candidate: the remembered one needs its exact distance too
           const long long w = T.order[single_pos];
-          best_d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
-          best_id = id_offset + w;
+          best.d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+          best.id = id_offset + w;
           single_pos = -1;
         }
-        unsigned mm = m;
-        while (mm) {
-          const int src_lane = __ffs(mm) - 1;
-          mm &= mm - 1;
-          const long long w = T.order[base + src_lane];
-          const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
-          const long long id = id_offset + w;
-          if (d < best_d || (d == best_d && id < best_id)) {
-            best_d = d;
-            best_id = id;
-          }
-        }
-        n += cnt;
+        best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m, base, qrow, sqq, id_offset, row_base, lane, best);
+        cnt += k;
       }
-      if (n == 1 && single_pos >= 0) {
+      qpg_bin_t rec;
+      if (cnt == 1 && single_pos >= 0) {
         rec.lo = best_lo;
-        rec.hi = Ug;
+        rec.hi = __longlong_as_double((long long)U);
         rec.id = id_offset + T.order[single_pos];
         rec.n = 1;
         rec.flags = 0;
       } else {
-        rec.lo = best_d;
-        rec.hi = best_d;
-        rec.id = best_id;
-        rec.n = n;                           // how many rows were re-evaluated (diagnostics)
-        rec.flags = 1;                       // exact
-        if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
+        rec.lo = best.d;
+        rec.hi = best.d;
+        rec.id = best.id;
+        rec.n = cnt;
+        rec.flags = 1;
+        if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)cnt);
       }
+      if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
     }
-    if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
-    if (consume && c == KB - 1)                  // rows with a label outside [0, 512) belong to no bin
-      for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
   }
+  if (consume && c == KB - 1)                    // rows with a label outside [0, 512) belong to no bin
+    for (int g = 0; g < ng; ++g)
+      for (long long pos = b1 + lane; pos < W; pos += 32) T.sacc[(size_t)(q0 + g) * Wpad + pos] = 0;
+}
+
+__global__ void __launch_bounds__(256, 3)
+    sliced_bins_kernel(const __grid_constant__ TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset,
+                       int64_t row_base, int consume, unsigned long long* __restrict__ stats) {
+  __shared__ QConst s_qc[BG];
+  __shared__ long long s_v[8 * BG * 32];         // [warp][query][lane] accumulators of the warp's bin
+  if (blockIdx.z == 0) bins_body(tp.t[0], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
+  else bins_body(tp.t[1], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
 }
 
 // ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
@@ -1018,8 +1087,7 @@ extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64
   const int rc = fill_tables(tabs, n_tabs, true, &tp);
   if (rc != QPG_OK) return rc;
   const long long Wpad = (W + TM - 1) / TM * TM;
-  const long long warps = (long long)((nq + BG - 1) / BG) * KB;
-  const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);
+  const dim3 grid(KB / 8, (unsigned)((nq + BG - 1) / BG), (unsigned)n_tabs);      // CTA = 8 start codes x 8 queries
   sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
                                                              reinterpret_cast<unsigned long long*>(stats));
   QPG_LAUNCH_CHECK();

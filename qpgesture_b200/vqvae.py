@@ -172,6 +172,16 @@ def _round_up(x, m):
     return (x + m - 1) // m * m
 
 
+_SM_COUNT = {}
+
+
+def _sm_count(device):
+    key = torch.device(device).index or 0
+    if key not in _SM_COUNT:
+        _SM_COUNT[key] = torch.cuda.get_device_properties(key).multi_processor_count
+    return _SM_COUNT[key]
+
+
 class _TcConv:
     """One launch of qpg_conv1d_taps_tf32.  `w_taps` is a list of [C_out, C_in] matrices (one per
     tap); they are stored [n_taps][N_pad][K_pad] zero padded, K-major, as the UMMA B operand."""
@@ -195,12 +205,34 @@ class _TcConv:
         self.bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
         self.row_offset, self.chan_offset = list(row_offset), list(chan_offset)
 
+    # relative time of one 128-row tile by width (measured: the main loop is shared-memory bound, a half-width tile
+    # costs 0.6 of a full one): narrower tiles pay only when the wide ones leave more than half of the SMs idle
+    _TILE_COST = {256: 1.0, 128: 0.6, 64: 0.38}
+
+    def _tile_n(self, B, n_out, device):
+        if self.BN not in self._TILE_COST:                       # ragged output widths keep their single tile
+            return self.BN
+        t_box = min(n_out, 128)
+        b_box = max(1, min(128 // t_box, B, 256))
+        tiles_m = -(-B // b_box) * -(-n_out // t_box)
+        sms = _sm_count(device)
+        best, best_cost = self.BN, None
+        for bn in (256, 128, 64):
+            if bn > self.BN or self.N_pad % bn:
+                continue
+            waves = -(-(tiles_m * (self.N_pad // bn)) // sms)
+            cost = waves * self._TILE_COST[bn]
+            if best_cost is None or cost < best_cost - 1e-9:
+                best, best_cost = bn, cost
+        return best
+
     def __call__(self, x, B, T_view, C_view, n_out, out=None, out_relu=None, residual=None, out_rows_per_item=None,
                  out_ld=None, out_chan_offset=0):
         lib = _lib.load()
         d = _lib.ConvTcDesc()
         d.B, d.T_view, d.C_view, d.n_out = B, T_view, C_view, n_out
-        d.C_in, d.C_out, d.K_pad, d.N_pad, d.BN, d.n_taps = self.c_in, self.c_out, self.K_pad, self.N_pad, self.BN, self.n_taps
+        d.C_in, d.C_out, d.K_pad, d.N_pad, d.BN, d.n_taps = self.c_in, self.c_out, self.K_pad, self.N_pad, \
+            self._tile_n(B, n_out, x.device), self.n_taps
         for i in range(4):
             d.row_offset[i] = self.row_offset[i] if i < self.n_taps else 0
             d.chan_offset[i] = self.chan_offset[i] if i < self.n_taps else 0

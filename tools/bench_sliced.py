@@ -73,6 +73,7 @@ def main():
         out["passes"] = len(p.passes)
         out["stats_per_step"] = [int(x) // (a.reps + 3 + 2) for x in p.stats.cpu().tolist()]
         sp = _lib.stream_ptr()
+        SP = [sp]                                            # the stream the stage functions launch on
         A, T = db.aud_s, db.txt_s
         ps = p.passes[0]
         jobs = (_lib.SliceJob * 2)()
@@ -87,13 +88,13 @@ def main():
         tabs_r = knn._sliced_tables(p, 0, p.Qt, 0, for_resolve=True)
 
         def slice_q():
-            lib.qpg_slice_queries_i8(jobs, 2, ps.nq, ps.n_pad, sp)
+            lib.qpg_slice_queries_i8(jobs, 2, ps.nq, ps.n_pad, SP[0])
 
         def scan():            # accumulates on top of earlier repetitions: timing only
-            lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, sp)
+            lib.qpg_sliced_scan_i8(segs, 2, A.W, ps.n_pad, ps.nq, SP[0])
 
         def scan_audio_only():
-            lib.qpg_sliced_scan_i8(segs, 1, A.W, ps.n_pad, ps.nq, sp)
+            lib.qpg_sliced_scan_i8(segs, 1, A.W, ps.n_pad, ps.nq, SP[0])
 
         def restore():         # a valid sacc for the stages behind the scan
             p.sacc_a.zero_()
@@ -101,32 +102,61 @@ def main():
             scan()
 
         def bins():            # consume = 0: the same valid sacc for every repetition
-            lib.qpg_sliced_bins(tabs_b, 2, A.W, ps.nq, db.id_offset, db.row_base, 0, None, sp)
+            lib.qpg_sliced_bins(tabs_b, 2, A.W, ps.nq, db.id_offset, db.row_base, 0, None, SP[0])
 
         def resolve():
-            lib.qpg_sliced_resolve(tabs_r, 2, 1, 2 * p.Q * 512, p.Qt, db.exact_offset, None, sp)
+            lib.qpg_sliced_resolve(tabs_r, 2, 1, 2 * p.Q * 512, p.Qt, db.exact_offset, None, SP[0])
 
         def lookup():
             lib.qpg_match_lookup(_lib.ptr(p.ta), _lib.ptr(p.tt), _lib.ptr(p.ra), _lib.ptr(p.rt), _lib.ptr(db.pos_rank_t), _lib.ptr(db.freq_rank),
                                  _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft),
-                                 p.Qt, _lib.ptr(p.entries), sp)
+                                 p.Qt, _lib.ptr(p.entries), SP[0])
 
         def walk_table():
             lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
-                               p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
+                               p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), SP[0])
 
         def walk_direct():
             lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
-                               p.n_tail, p.n_seg, None, _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), sp)
+                               p.n_tail, p.n_seg, None, _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), SP[0])
+        def timed_graph(fn, reps=20):
+            """device time per launch with the host out of the loop: `reps` launches captured into one CUDA graph
+            (the Python/ctypes launch path costs 15-30 us per call, more than most of these kernels take)"""
+            st = torch.cuda.Stream()
+            st.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(st):
+                SP[0] = _lib.stream_ptr(st)
+                fn()
+                st.synchronize()
+                gr = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gr, stream=st):
+                    SP[0] = _lib.stream_ptr()
+                    for _ in range(reps):
+                        fn()
+                gr.replay()
+                st.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(st)
+                for _ in range(5):
+                    gr.replay()
+                e1.record(st)
+                st.synchronize()
+            SP[0] = sp
+            torch.cuda.current_stream().wait_stream(st)
+            return e0.elapsed_time(e1) / (5 * reps) * 1e3
+
         out["stage_us"] = {}
+        out["stage_us_graph"] = {}
         for name, f in (("slice_queries", slice_q), ("scan", scan), ("scan_audio_only", scan_audio_only)):
             out["stage_us"][name] = timed(f)
+            out["stage_us_graph"][name] = timed_graph(f)
         restore()
         stages = [("bins", bins), ("resolve", resolve), ("lookup", lookup), ("walk_direct", walk_direct)]
         if p.trans is not None:
             stages.append(("walk_table", walk_table))
         for name, f in stages:
             out["stage_us"][name] = timed(f)
+            out["stage_us_graph"][name] = timed_graph(f)
         p.sacc_a.zero_()
         p.sacc_t.zero_()
         sliced_bytes = A.nbytes + T.nbytes
