@@ -755,6 +755,131 @@ __global__ void __launch_bounds__(256, 3)
   else bins_body(tp.t[1], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
 }
 
+// Long bins (all-speaker tables and the synthetic sweeps: hundreds to thousands of rows per start code): the first
+// version of the kernel, one warp per (table, start code, four queries) with the four sacc loads of a lane in flight
+// together on both trips over the bin - the one-trip kernel above is sequential per query on such bins.
+constexpr int BGL = 4;
+__global__ void __launch_bounds__(256, 2)
+    sliced_bins_long_kernel(const __grid_constant__ TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset, int64_t row_base,
+                       int consume, unsigned long long* __restrict__ stats) {
+  const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
+  const int lane = threadIdx.x & 31;
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int n_groups = (nq + BGL - 1) / BGL;
+  if (wid >= (long long)n_groups * KB) return;
+  const int q0 = (int)(wid / KB) * BGL, c = (int)(wid % KB);
+  const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
+  QConst qi[BGL];
+#pragma unroll
+  for (int g = 0; g < BGL; ++g) qi[g] = make_qconst(T.q_info[min(q0 + g, nq - 1)]);
+  double U[BGL], lo0[BGL], hi0[BGL];
+#pragma unroll
+  for (int g = 0; g < BGL; ++g) {
+    U[g] = 1e300;
+    lo0[g] = hi0[g] = 0.0;
+  }
+  // pass 1: U per query; the intervals of the first 32 rows (most bins have no more) stay in registers
+  for (int pos = b0 + lane; pos < b1; pos += 32) {
+    const RowInfo ri = T.row_info[pos];
+    long long v[BGL];
+#pragma unroll
+    for (int g = 0; g < BGL; ++g) v[g] = T.sacc[(size_t)min(q0 + g, nq - 1) * Wpad + pos];
+#pragma unroll
+    for (int g = 0; g < BGL; ++g) {
+      const Interval iv = filter_interval(v[g], ri, qi[g]);
+      if (pos < b0 + 32) {
+        lo0[g] = iv.lo;
+        hi0[g] = iv.hi;
+      }
+      U[g] = fmin(U[g], iv.hi);
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < BGL; ++g)
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) U[g] = fmin(U[g], __shfl_xor_sync(0xffffffffu, U[g], o));
+
+#pragma unroll 1
+  for (int g = 0; g < BGL; ++g) {
+    const int qi_ = q0 + g;
+    if (qi_ >= nq) break;
+    long long* sv = T.sacc + (size_t)qi_ * Wpad;
+    const float* qrow = T.q + (size_t)qi_ * T.ldq;
+    const QConst qg = g == 0 ? qi[0] : g == 1 ? qi[1] : g == 2 ? qi[2] : qi[3];
+    const double sqq = T.q_info[qi_].sq;
+    const double Ug = g == 0 ? U[0] : g == 1 ? U[1] : g == 2 ? U[2] : U[3];
+    const double l0 = g == 0 ? lo0[0] : g == 1 ? lo0[1] : g == 2 ? lo0[2] : lo0[3];
+    qpg_bin_t rec;
+    rec.lo = kEmptyDist;
+    rec.hi = kEmptyDist;
+    rec.id = -1;
+    rec.n = 0;
+    rec.flags = 1;                               // empty bins are exact (sentinel)
+    if (b1 > b0) {
+      int n = 0;
+      double best_lo = 1e300, best_d = 1e300;
+      long long best_id = -1, single_pos = -1;
+      for (int base = b0; base < b1; base += 32) {
+        const int pos = base + lane;
+        bool cand = false;
+        double lo = 0.0;
+        if (pos < b1) {
+          lo = base == b0 ? l0 : filter_interval(sv[pos], T.row_info[pos], qg).lo;
+          cand = lo <= Ug;
+          if (consume) sv[pos] = 0;
+        }
+        const unsigned m = __ballot_sync(0xffffffffu, cand);
+        const int cnt = __popc(m);
+        if (cnt == 0) continue;
+        if (n == 0 && cnt == 1) {          // remember the first lone candidate; verified only if another shows up
+          const int src_lane = __ffs(m) - 1;
+          single_pos = base + src_lane;
+          best_lo = __shfl_sync(0xffffffffu, lo, src_lane);
+          n = 1;
+          continue;
+        }
+        // more than one candidate so far: evaluate exactly (including the remembered one)
+        if (n == 1 && single_pos >= 0) {
+          const long long w = T.order[single_pos];
+          best_d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+          best_id = id_offset + w;
+          single_pos = -1;
+        }
+        unsigned mm = m;
+        while (mm) {
+          const int src_lane = __ffs(mm) - 1;
+          mm &= mm - 1;
+          const long long w = T.order[base + src_lane];
+          const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+          const long long id = id_offset + w;
+          if (d < best_d || (d == best_d && id < best_id)) {
+            best_d = d;
+            best_id = id;
+          }
+        }
+        n += cnt;
+      }
+      if (n == 1 && single_pos >= 0) {
+        rec.lo = best_lo;
+        rec.hi = Ug;
+        rec.id = id_offset + T.order[single_pos];
+        rec.n = 1;
+        rec.flags = 0;
+      } else {
+        rec.lo = best_d;
+        rec.hi = best_d;
+        rec.id = best_id;
+        rec.n = n;                           // how many rows were re-evaluated (diagnostics)
+        rec.flags = 1;                       // exact
+        if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)n);
+      }
+    }
+    if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
+    if (consume && c == KB - 1)                  // rows with a label outside [0, 512) belong to no bin
+      for (long long pos = b1 + lane; pos < W; pos += 32) sv[pos] = 0;
+  }
+}
+
 // ------------------------------------------------------------------ resolve: merge parts, decide, verify, rank
 // One CTA (512 threads, thread = start code) per (table, query).  T.bins points at part 0; part p is
 // part_stride records further (P = 1 on a single GPU, the all-gathered per-rank records when database rows are
@@ -1087,9 +1212,16 @@ extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64
   const int rc = fill_tables(tabs, n_tabs, true, &tp);
   if (rc != QPG_OK) return rc;
   const long long Wpad = (W + TM - 1) / TM * TM;
-  const dim3 grid(KB / 8, (unsigned)((nq + BG - 1) / BG), (unsigned)n_tabs);      // CTA = 8 start codes x 8 queries
-  sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
-                                                             reinterpret_cast<unsigned long long*>(stats));
+  if (W <= 32 * KB) {                          // bins of about one warp of rows: settled in one trip
+    const dim3 grid(KB / 8, (unsigned)((nq + BG - 1) / BG), (unsigned)n_tabs);    // CTA = 8 start codes x 8 queries
+    sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
+                                                               reinterpret_cast<unsigned long long*>(stats));
+  } else {
+    const long long warps = (long long)((nq + BGL - 1) / BGL) * KB;
+    const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);
+    sliced_bins_long_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
+                                                                    reinterpret_cast<unsigned long long*>(stats));
+  }
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
