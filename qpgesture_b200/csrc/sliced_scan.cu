@@ -924,16 +924,17 @@ __device__ __forceinline__ void bitonic_sort_512(unsigned long long* key, int* v
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(KB)
+__global__ void __launch_bounds__(KB, 2)
     sliced_resolve_kernel(const TablePair tp, int P, long long part_stride, int64_t first_id,
                           unsigned long long* __restrict__ stats) {
-  __shared__ unsigned long long s_key[KB];       // sort keys: lo bits (first sort), final distance bits (second)
+  __shared__ unsigned long long s_key[KB];       // interval starts (bit patterns), sorted
   __shared__ int s_val[KB];
   __shared__ unsigned long long s_hi[KB];        // hi bits by code, then running maximum by sorted position
   __shared__ unsigned long long s_pm[KB];
   __shared__ unsigned long long s_d[KB];
   __shared__ long long s_id[KB];
-  __shared__ int s_ov[KB], s_list[KB];
+  __shared__ int s_ov[KB], s_list[KB], s_link[KB];
+  __shared__ unsigned long long s_wmax[KB / 32];
   __shared__ int s_n, s_tie;
   const TableParams T = blockIdx.y == 0 ? tp.t[0] : tp.t[1];
   const qpg_bin_t* __restrict__ parts = T.bins;
@@ -976,25 +977,31 @@ __global__ void __launch_bounds__(KB)
   s_hi[c] = hi_b;
   __syncthreads();
   bitonic_sort_512(s_key, s_val, c);             // by interval start
-  // running maximum of the interval ends in sorted order (Hillis-Steele)
+  // running maximum of the interval ends in sorted order: shuffle scan inside each warp, then the warp totals
   unsigned long long pm = s_hi[s_val[c]];
   const unsigned long long my_hi_sorted = pm;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned long long prev = __shfl_up_sync(0xffffffffu, pm, o);
+    if (lane >= o && prev > pm) pm = prev;
+  }
+  if (lane == 31) s_wmax[warp] = pm;
   __syncthreads();
+  {
+    unsigned long long before = 0ull;
+    for (int w = 0; w < warp; ++w) before = s_wmax[w] > before ? s_wmax[w] : before;
+    if (before > pm) pm = before;
+  }
   s_pm[c] = pm;
   __syncthreads();
-  for (int o = 1; o < KB; o <<= 1) {
-    const unsigned long long prev = c >= o ? s_pm[c - o] : 0ull;
-    __syncthreads();
-    pm = prev > pm ? prev : pm;
-    s_pm[c] = pm;
-    __syncthreads();
-  }
   {
     // sorted position c: does this bin's interval touch another one?  (empty bins sort last and touch nothing)
     const bool nonempty = my_hi_sorted < empty_bits;
     const bool right = c + 1 < KB && s_key[c + 1] <= my_hi_sorted;
     const bool left = c > 0 && s_pm[c - 1] >= s_key[c];
     s_ov[s_val[c]] = nonempty && (left || right);
+    // positions c and c + 1 belong to one cluster of (transitively) overlapping intervals
+    s_link[c] = nonempty && c + 1 < KB && s_key[c + 1] < empty_bits && s_pm[c] >= s_key[c + 1];
   }
   __syncthreads();
   // a bin needs a float64 decision when several shards could hold its winner, or when its interval overlaps
@@ -1035,18 +1042,35 @@ __global__ void __launch_bounds__(KB)
   }
   __syncthreads();
   if (c == 0 && stats) atomicAdd(&stats[1], (unsigned long long)n_list);
-  // stable rank (ties -> lower code first) = position in the order by (distance, code); tie flag among non-empty bins
-  const unsigned long long mine = s_d[c];
-  s_key[c] = mine;
-  s_val[c] = c;
-  __syncthreads();
-  bitonic_sort_512(s_key, s_val, c);
+  // stable rank (ties -> lower code first) = position in the order by (distance, code).  Intervals that touch
+  // nothing are already in that order (sorted by interval start; the true distance lies inside the interval), so
+  // their rank is their sorted position: no second sort.  A cluster of touching intervals is a contiguous run of
+  // sorted positions whose members all carry exact distances now; they are ranked among themselves.  Equal
+  // distances (the tie flag) can only occur inside a cluster.
   {
-    const unsigned long long k = s_key[c];
-    const bool tie = k != empty_bits && ((c + 1 < KB && s_key[c + 1] == k) || (c > 0 && s_key[c - 1] == k));
-    if (tie) s_tie = 1;
-    T.ranks[(size_t)qi_ * KB + s_val[c]] = c;
+    const int code = s_val[c];
+    int rank = c;
+    const bool in_cluster = s_link[c] || (c > 0 && s_link[c - 1]);
+    if (in_cluster) {
+      const unsigned long long dp = s_d[code];
+      int start = c;
+      while (start > 0 && s_link[start - 1]) --start;
+      int smaller = 0, tie = 0;
+      for (int m = start;; ++m) {
+        if (m != c) {
+          const int cm = s_val[m];
+          const unsigned long long dm = s_d[cm];
+          smaller += (dm < dp) || (dm == dp && cm < code);
+          tie |= dm == dp;
+        }
+        if (m + 1 >= KB || !s_link[m]) break;
+      }
+      rank = start + smaller;
+      if (tie) s_tie = 1;
+    }
+    T.ranks[(size_t)qi_ * KB + code] = rank;
   }
+  const unsigned long long mine = s_d[c];
   Pair out;
   out.d = mine;
   out.id = (unsigned long long)s_id[c];
