@@ -297,6 +297,20 @@ int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* txt_table, c
 int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp, const int32_t* seed_code,
                    const float* seed_phase, int n_clips, int n_seg, int16_t* trans, int64_t* codes_out,
                    int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream);
+/* Per-(window, table) phase statistics, built once per database: for window w = 26*sequence + m and table x
+ * (0 audio, 1 text) the 72 floats at stats[(2*w + x)*72] hold the squared norms and self-dots of the rows the
+ * phase pick (GestureKNN.py:636,:644) takes from that window as a candidate (rows 0..4 behind its phase frame) and
+ * as the previous winner (rows 27..31), plus the four rows of the cross term.  stats: 16-byte aligned,
+ * n_seq * 26 * 2 * qpg_phase_stats_floats() floats.
+ * qpg_match_walk_stats = qpg_match_walk whose transition pass (trans != NULL) reads that table: the float32 filter of
+ * a state is then 64 multiply-adds by eight lanes (four states per warp) instead of two 128-element cosines by a
+ * whole warp; undecided states take the same float64 pick.  Identical results. */
+size_t qpg_phase_stats_floats(void);
+int qpg_phase_stats(const float* phase_amp, int64_t n_seq, const int32_t* aud_frame, const int32_t* txt_frame,
+                    float* stats, void* stream);
+int qpg_match_walk_stats(const void* entries, const int32_t* code, const float* phase_amp, const float* phase_stats,
+                         const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg, int16_t* trans,
+                         int64_t* codes_out, int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream);
 
 /* ---------------- VQ codebook L2 argmin -----------------------------------
  * BottleneckBlock.quantise (codebook/models/bottleneck.py:120-126):

@@ -27,7 +27,7 @@ import torch
 from . import _lib
 from .constant import (NUM_AUDIO_FEAT_FRAMES, SEED_VALUE, STEP_SZ, STEPS_PER_SEGMENT, WINDOWS_PER_SEQ, codebook_size,
                        num_frames, num_frames_code)
-from .matchdb import (MatchDatabase, new_table, pad_tokens, phase_to_dense, table_to_numpy, wavvq_tokens)
+from .matchdb import (MatchDatabase, ensure_phase_stats, new_table, pad_tokens, phase_to_dense, table_to_numpy, wavvq_tokens)
 
 args = None  # module-global like the reference's (GestureKNN.py:41); set by main()/set_args()
 
@@ -390,6 +390,8 @@ class CodeKNN(object):
             p.vote = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT), dtype=torch.int32, device=dev)
             p.phase = torch.empty((n_tail, n_seg, STEPS_PER_SEGMENT, 8, 16), dtype=torch.float32, device=dev) \
                 if want_phase else None
+            # the table walk's transition kernel reads per-window phase statistics (built once per database)
+            p.phase_stats = ensure_phase_stats(db) if p.trans is not None else None
             p.scan_stream = torch.cuda.Stream(device=dev, priority=-1) if scan_priority else None
             if use_graph:
                 self._launch_plan(p)                       # warm-up outside capture (sets function attributes)
@@ -518,9 +520,10 @@ class CodeKNN(object):
                                         _lib.ptr(db.freq_rank), _lib.ptr(db.code), db.n_seq, _lib.ptr(db.aud_frame),
                                         _lib.ptr(db.txt_frame), _lib.ptr(p.qfa), _lib.ptr(p.qft), p.Qt,
                                         _lib.ptr(p.entries), sp), "qpg_match_lookup")
-        _lib.check(lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(sc),
-                                      _lib.ptr(sph), p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes),
-                                      _lib.ptr(p.vote), _lib.ptr(p.phase), _lib.ptr(p.status), sp), "qpg_match_walk")
+        _lib.check(lib.qpg_match_walk_stats(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp),
+                                            _lib.ptr(p.phase_stats), _lib.ptr(sc), _lib.ptr(sph), p.n_tail, p.n_seg,
+                                            _lib.ptr(p.trans), _lib.ptr(p.codes), _lib.ptr(p.vote), _lib.ptr(p.phase),
+                                            _lib.ptr(p.status), sp), "qpg_match_walk_stats")
 
     def make_pipeline(self, n_clips: int, n_seg: int, depth: int = 3, **plan_kwargs):
         """`depth` independent plans, each with its own stream, buffers, captured graph and pinned host mirrors:

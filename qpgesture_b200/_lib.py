@@ -85,6 +85,9 @@ SIGNATURES = {
     "qpg_sliced_resolve": (_INT, [_P, _INT, _INT, _I64, _INT, _I64, _P, _P]),
     "qpg_match_lookup": (_INT, [_P, _P, _P, _P, _P, _P, _P, _I64, _P, _P, _P, _P, _INT, _P, _P]),
     "qpg_match_walk": (_INT, [_P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P, _P]),
+    "qpg_match_walk_stats": (_INT, [_P, _P, _P, _P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P, _P]),
+    "qpg_phase_stats_floats": (C.c_size_t, []),
+    "qpg_phase_stats": (_INT, [_P, _I64, _P, _P, _P, _P]),
     "qpg_cand_lev_minbycode": (_INT, [_P, _P, _I64, _I64, _P, _INT, _P, _P]),
     "qpg_lev_distance": (_INT, [_P, _P, _I64, _P, _P]),
     "qpg_l2_prefetch": (_INT, [_P, C.c_size_t, _P]),

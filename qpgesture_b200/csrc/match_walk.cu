@@ -400,6 +400,174 @@ __global__ void __launch_bounds__(256, 6)
 
 // one CTA per clip: the clip's transition table goes to shared memory, one thread follows it, then all threads
 // write the outputs of the visited states
+// ---- transitions from per-window phase statistics: four states per warp ------------------------------------
+// The two vectors of the pick are a = [prev rows 3..7; head rows 0..2] and b = [prev rows 5..7; head rows 0..4]
+// (prev = rows 24..31 behind the previous winner's phase frame, head = rows behind the candidate's), so
+//   |a|^2 = T5(prev) + H3(cand),  |b|^2 = T3(prev) + H5(cand),
+//   a.b   = TT(prev) + [prev row 6 . head row 0 + prev row 7 . head row 1] + HH(cand)
+// where T5, T3, TT depend on the previous window only and H3, H5, HH on the candidate only.  qpg_phase_stats
+// tabulates them once per (window, table) together with the four rows of the cross term (72 floats), so the
+// float32 filter of a state is 2 x 32 multiply-adds and two scalar loads: eight lanes per state instead of a warp,
+// no phase_amp access, no window-id division.  States whose two distances are within 1e-3 (or whose sums are not
+// trustworthy in float32) take the float64 pick of match_transition_kernel, a warp at a time.
+constexpr int PSTAT = 72;                 // floats per (window, table): 8 scalars, head rows 0-1, tail rows 30-31
+
+__global__ void __launch_bounds__(256)
+    phase_stats_kernel(const float* __restrict__ phase_amp, long long n_windows, const int32_t* __restrict__ aud_frame,
+                       const int32_t* __restrict__ txt_frame, float* __restrict__ stats) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;   // (window, table)
+  if (wid >= n_windows * 2) return;
+  const int lane = threadIdx.x & 31, hl = lane & 15, x = (int)(wid & 1);
+  const long long w = wid >> 1, j = w / WIN;
+  const int m = (int)(w - j * WIN);
+  const int f = (x == 0 ? aud_frame : txt_frame)[m];
+  const float* rows = phase_amp + ((size_t)j * NFRM + f) * PC;
+  float* out = stats + (size_t)wid * PSTAT;
+  // lanes 0-15: head rows 0..4, lanes 16-31: tail rows 27..31 (= prev rows 3..7); lane hl owns column hl
+  const int r0 = lane < 16 ? 0 : 27;
+  float v[5];
+#pragma unroll
+  for (int k = 0; k < 5; ++k) v[k] = (f + r0 + k < NFRM) ? rows[(r0 + k) * PC + hl] : 0.f;
+  // head: H3 = |rows 0..2|^2, H5 = |rows 0..4|^2, HH = r0.r2 + r1.r3 + r2.r4
+  // tail: T5 = |rows 27..31|^2, T3 = |rows 29..31|^2, TT = r27.r29 + r28.r30 + r29.r31
+  float s3, s5, sd;
+  if (lane < 16) {
+    s3 = v[0] * v[0] + v[1] * v[1] + v[2] * v[2];
+    s5 = s3 + v[3] * v[3] + v[4] * v[4];
+  } else {
+    s3 = v[2] * v[2] + v[3] * v[3] + v[4] * v[4];
+    s5 = s3 + v[0] * v[0] + v[1] * v[1];
+  }
+  sd = v[0] * v[2] + v[1] * v[3] + v[2] * v[4];
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) {
+    s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+    s5 += __shfl_xor_sync(0xffffffffu, s5, o);
+    sd += __shfl_xor_sync(0xffffffffu, sd, o);
+  }
+  if (lane == 0) {
+    out[0] = s3;
+    out[1] = s5;
+    out[2] = sd;
+    out[3] = 0.f;
+  }
+  if (lane == 16) {
+    out[4] = s5;      // T5
+    out[5] = s3;      // T3
+    out[6] = sd;      // TT
+    out[7] = 0.f;
+  }
+  if (lane < 16) {
+    out[8 + hl] = v[0];
+    out[24 + hl] = v[1];
+  } else {
+    out[40 + hl] = v[3];      // row 30 = prev row 6
+    out[56 + hl] = v[4];      // row 31 = prev row 7
+  }
+}
+
+__global__ void __launch_bounds__(256, 4)
+    match_transition_fast_kernel(const Entry* __restrict__ entries, const float* __restrict__ stats,
+                                 const float* __restrict__ phase_amp, const int32_t* __restrict__ seed_code,
+                                 const float* __restrict__ seed_phase, int n_steps, long long n_states,
+                                 int16_t* __restrict__ trans) {
+  const long long wid = (blockIdx.x * (long long)blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31, grp = lane >> 3, gl = lane & 7;
+  const long long sid = wid * 4 + grp;                 // (step, state) of this group of eight lanes
+  if (wid * 4 >= n_states) return;
+  const bool live = sid < n_states;
+  const long long q = (live ? sid : n_states - 1) >> 10;
+  const int state = (int)((live ? sid : n_states - 1) & 1023);
+  const int st = (int)(q % n_steps);
+  const long long b = q / n_steps;
+  // result: >= 0 decided, -1/-2/-3 as match_transition_kernel, kSlow = needs the float64 pick
+  constexpr int kSlow = -100;
+  int result = kSlow, last = 0, eflag = 0, fp = 0, f0 = 0, f1 = 0;
+  long long wp = -1, w0 = -1, w1 = -1;
+  if (st == 0) {
+    if (state != 0) result = -2;
+    else {
+      last = seed_code[b];
+      if ((unsigned)last >= (unsigned)KB) result = -1;
+    }
+  } else {
+    const Entry ep = load_entry(entries + (q - 1) * KB + (state >> 1));
+    const int xp = state & 1;
+    if (ep.w[0] < 0 || ep.w[1] < 0) result = -2;      // the previous step raised: nothing continues from it
+    else {
+      wp = xp == 0 ? ep.w[0] : ep.w[1];
+      fp = xp == 0 ? ep.frame[0] : ep.frame[1];
+      last = (st & 7) == 0 ? (xp == 0 ? ep.nls[0] : ep.nls[1]) : (xp == 0 ? ep.nl[0] : ep.nl[1]);
+    }
+  }
+  if (result == kSlow) {
+    const Entry e = load_entry(entries + q * KB + last);
+    eflag = e.flags & 1;
+    if (e.w[0] < 0 || e.w[1] < 0) result = eflag ? -3 : -1;       // IndexError (tie dependent: -3)
+    else {
+      w0 = e.w[0];
+      w1 = e.w[1];
+      f0 = e.frame[0];
+      f1 = e.frame[1];
+    }
+  }
+  {
+    // float32 filter from the tables: lanes 0-3 of the group score the audio candidate, lanes 4-7 the text one.
+    // Executed by every lane (groups without a live pick read window 0) so that the shuffles stay warp-uniform.
+    const bool use = result == kSlow && st != 0;
+    const int x = gl >> 2, c4 = (gl & 3) * 4;
+    const float* P = stats + ((size_t)(use ? wp : 0) * 2 + (state & 1)) * PSTAT;
+    const float* C = stats + ((size_t)(use ? (x == 0 ? w0 : w1) : 0) * 2 + x) * PSTAT;
+    const float4 t6 = __ldg(reinterpret_cast<const float4*>(P + 40 + c4)), t7 = __ldg(reinterpret_cast<const float4*>(P + 56 + c4));
+    const float4 h0 = __ldg(reinterpret_cast<const float4*>(C + 8 + c4)), h1 = __ldg(reinterpret_cast<const float4*>(C + 24 + c4));
+    const float4 ps = __ldg(reinterpret_cast<const float4*>(P + 4)), cs = __ldg(reinterpret_cast<const float4*>(C));
+    float xs = t6.x * h0.x;
+    xs = fmaf(t6.y, h0.y, xs);
+    xs = fmaf(t6.z, h0.z, xs);
+    xs = fmaf(t6.w, h0.w, xs);
+    xs = fmaf(t7.x, h1.x, xs);
+    xs = fmaf(t7.y, h1.y, xs);
+    xs = fmaf(t7.z, h1.z, xs);
+    xs = fmaf(t7.w, h1.w, xs);
+    xs += __shfl_xor_sync(0xffffffffu, xs, 1);
+    xs += __shfl_xor_sync(0xffffffffu, xs, 2);
+    const float sa = ps.x + cs.x, sb = ps.y + cs.y, ab = ps.z + xs + cs.z;
+    const float ia = sa > 0.f ? rsqrtf(sa) : 0.f, ib = sb > 0.f ? rsqrtf(sb) : 0.f;
+    const float d32 = 0.5f * ((sa > 0.f ? 1.f : 0.f) + (sb > 0.f ? 1.f : 0.f)) - ab * ia * ib;
+    const int sane = (sa < 1e30f && sb < 1e30f && (sa == 0.f || sa > 1e-30f) && (sb == 0.f || sb > 1e-30f)) ? 1 : 0;
+    const float da = __shfl_sync(0xffffffffu, d32, lane & ~7), dt = __shfl_sync(0xffffffffu, d32, (lane & ~7) + 4);
+    const int sane_a = __shfl_sync(0xffffffffu, sane, lane & ~7), sane_t = __shfl_sync(0xffffffffu, sane, (lane & ~7) + 4);
+    if (use && sane_a && sane_t && fabsf(da - dt) > 1e-3f) result = (last << 1) | (da < dt ? 0 : 1) | (eflag << 10);
+  }
+  // undecided states: the float64 pick, one state at a time by the whole warp
+  unsigned need = __ballot_sync(0xffffffffu, live && result == kSlow && gl == 0);
+  while (need) {
+    const int src = __ffs(need) - 1;
+    need &= need - 1;
+    const int s_st = __shfl_sync(0xffffffffu, st, src), s_last = __shfl_sync(0xffffffffu, last, src);
+    const int s_flag = __shfl_sync(0xffffffffu, eflag, src);
+    const long long s_b = __shfl_sync(0xffffffffu, b, src), s_wp = __shfl_sync(0xffffffffu, wp, src);
+    const long long s_w0 = __shfl_sync(0xffffffffu, w0, src), s_w1 = __shfl_sync(0xffffffffu, w1, src);
+    const int s_fp = __shfl_sync(0xffffffffu, fp, src), s_f0 = __shfl_sync(0xffffffffu, f0, src);
+    const int s_f1 = __shfl_sync(0xffffffffu, f1, src);
+    const int hw = lane >> 4, hl = lane & 15;
+    float prev5[5];
+    if (s_st == 0) {
+#pragma unroll
+      for (int k = 0; k < 5; ++k) prev5[k] = seed_phase[(size_t)s_b * 8 * PC + (3 + k) * PC + hl];
+    } else {
+      const float* tailp = phase_amp + ((size_t)(s_wp / WIN) * NFRM + s_fp + 24) * PC;
+#pragma unroll
+      for (int k = 0; k < 5; ++k) prev5[k] = tailp[(3 + k) * PC + hl];
+    }
+    const long long w = hw == 0 ? s_w0 : s_w1;
+    const int f = hw == 0 ? s_f0 : s_f1;
+    const int win = phase_pick(prev5, phase_amp + ((size_t)(w / WIN) * NFRM + f) * PC, lane);
+    if (lane == src) result = (s_last << 1) | win | (s_flag << 10);
+  }
+  if (live && gl == 0) trans[sid] = (int16_t)result;
+}
+
 constexpr int WALK_MAX_STEPS = 104;                  // 104 * 2 KiB = 208 KiB of shared memory
 __global__ void __launch_bounds__(256)
     match_table_walk_kernel(const int16_t* __restrict__ trans, const Entry* __restrict__ entries,
@@ -484,10 +652,9 @@ extern "C" int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* t
   return QPG_OK;
 }
 
-extern "C" int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp,
-                              const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg,
-                              int16_t* trans, int64_t* codes_out, int32_t* vote_out, float* phase_out,
-                              int32_t* status_out, void* stream) {
+static int walk_impl(const void* entries, const int32_t* code, const float* phase_amp, const float* phase_stats,
+                     const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg, int16_t* trans,
+                     int64_t* codes_out, int32_t* vote_out, float* phase_out, int32_t* status_out, void* stream) {
   QPG_CHECK_ARG(n_clips >= 0 && n_seg >= 0, "negative size");
   if (n_clips == 0 || n_seg == 0) return QPG_OK;
   QPG_CHECK_ARG(entries && code && phase_amp && seed_code && seed_phase && codes_out && vote_out && status_out,
@@ -496,9 +663,16 @@ extern "C" int qpg_match_walk(const void* entries, const int32_t* code, const fl
   const int n_steps = n_seg * 8;
   if (trans != nullptr && n_steps <= WALK_MAX_STEPS) {
     QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(trans) & 15) == 0, "trans must be 16-byte aligned");
-    const long long n_warps = (long long)n_clips * n_steps * 1024;
-    match_transition_kernel<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const Entry*>(entries), phase_amp, seed_code, seed_phase, n_steps, n_warps, trans);
+    const long long n_states = (long long)n_clips * n_steps * 1024;
+    if (phase_stats) {
+      QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(phase_stats) & 15) == 0, "phase_stats must be 16-byte aligned");
+      const long long n_warps = (n_states + 3) / 4;
+      match_transition_fast_kernel<<<(unsigned)((n_warps * 32 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const Entry*>(entries), phase_stats, phase_amp, seed_code, seed_phase, n_steps, n_states, trans);
+    } else {
+      match_transition_kernel<<<(unsigned)((n_states * 32 + 255) / 256), 256, 0, st>>>(
+          reinterpret_cast<const Entry*>(entries), phase_amp, seed_code, seed_phase, n_steps, n_states, trans);
+    }
     QPG_LAUNCH_CHECK();
     const size_t smem = (size_t)n_steps * 2048;
     QPG_CUDA(cudaFuncSetAttribute(match_table_walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -509,6 +683,37 @@ extern "C" int qpg_match_walk(const void* entries, const int32_t* code, const fl
   }
   match_walk_kernel<<<n_clips, 32, 0, st>>>(reinterpret_cast<const Entry*>(entries), code, phase_amp, seed_code,
                                             seed_phase, n_seg, codes_out, vote_out, phase_out, status_out);
+  QPG_LAUNCH_CHECK();
+  return QPG_OK;
+}
+
+extern "C" int qpg_match_walk(const void* entries, const int32_t* code, const float* phase_amp,
+                              const int32_t* seed_code, const float* seed_phase, int n_clips, int n_seg,
+                              int16_t* trans, int64_t* codes_out, int32_t* vote_out, float* phase_out,
+                              int32_t* status_out, void* stream) {
+  return walk_impl(entries, code, phase_amp, nullptr, seed_code, seed_phase, n_clips, n_seg, trans, codes_out, vote_out,
+                   phase_out, status_out, stream);
+}
+
+extern "C" int qpg_match_walk_stats(const void* entries, const int32_t* code, const float* phase_amp,
+                                    const float* phase_stats, const int32_t* seed_code, const float* seed_phase,
+                                    int n_clips, int n_seg, int16_t* trans, int64_t* codes_out, int32_t* vote_out,
+                                    float* phase_out, int32_t* status_out, void* stream) {
+  return walk_impl(entries, code, phase_amp, phase_stats, seed_code, seed_phase, n_clips, n_seg, trans, codes_out,
+                   vote_out, phase_out, status_out, stream);
+}
+
+extern "C" size_t qpg_phase_stats_floats(void) { return PSTAT; }
+
+extern "C" int qpg_phase_stats(const float* phase_amp, int64_t n_seq, const int32_t* aud_frame, const int32_t* txt_frame,
+                               float* stats, void* stream) {
+  QPG_CHECK_ARG(n_seq >= 0, "negative size");
+  if (n_seq == 0) return QPG_OK;
+  QPG_CHECK_ARG(phase_amp && aud_frame && txt_frame && stats, "null pointer");
+  QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(stats) & 15) == 0, "stats must be 16-byte aligned");
+  const long long n_windows = (long long)n_seq * WIN;
+  phase_stats_kernel<<<(unsigned)((n_windows * 2 * 32 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      phase_amp, n_windows, aud_frame, txt_frame, stats);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }

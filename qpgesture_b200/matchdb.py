@@ -342,6 +342,21 @@ class MatchDatabase:
 _PACKED_VERSION = 2
 
 
+def ensure_phase_stats(db):
+    """Per-(window, table) phase statistics for the transition kernel (csrc/match_walk.cu, qpg_phase_stats): the
+    squared norms and self-dots of the head / tail rows of the window's phase frame and the four rows of the cross
+    term, 72 floats each.  Built once per database on the device (7.7 MB for the speaker-10 table)."""
+    if getattr(db, "phase_stats", None) is None:
+        lib = _lib.load()
+        n = int(db.phase_amp.shape[0])
+        stats = torch.empty((n * WINDOWS_PER_SEQ * 2 * int(lib.qpg_phase_stats_floats()),), dtype=torch.float32,
+                            device=db.phase_amp.device)
+        _lib.check(lib.qpg_phase_stats(_lib.ptr(db.phase_amp), n, _lib.ptr(db.aud_frame), _lib.ptr(db.txt_frame),
+                                       _lib.ptr(stats), _lib.stream_ptr()), "qpg_phase_stats")
+        db.phase_stats = stats
+    return db.phase_stats
+
+
 def save_packed_db(path: str, mode: str, code, signature, phase_amp, txt_rows, aud_rows=None, aud_tokens=None,
                    freq_code=None, device=None) -> None:
     """Row 8(f).1: one-file database for the matcher.  Everything load_db_codebook + CodeKNN.__init__ derive at

@@ -328,6 +328,10 @@ def test_lookup_walk_equals_round1_tail():
     Q = n_clips * n_seg * 8
     code = rng.integers(0, 512, size=(n_seq, 30)).astype(np.int32)
     phase = rng.standard_normal((n_seq, 240, 16)).astype(np.float32)
+    phase[6] = phase[5]                                       # equal candidates: exact distance ties (audio wins)
+    phase[7] = 0.0                                            # all-zero phase vectors
+    phase[8] *= np.float32(1e-21)                             # squares underflow in float32: float64 pick only
+    phase[9] = phase[10] * np.float32(1.0 + 3e-4)             # distances closer than the filter's 1e-3 margin
     pos_rank = np.stack([rng.permutation(512) for _ in range(512)]).astype(np.int32)
     freq_rank = rng.permutation(512).astype(np.int32)
     frames_a = np.array([int(6 * m / 398 * 240) for m in range(26)], dtype=np.int32)
@@ -355,8 +359,12 @@ def test_lookup_walk_equals_round1_tail():
     qft = torch.empty((Q,), dtype=torch.int32, device=dev)
     _lib.check(lib.qpg_rank512_ties(_lib.ptr(ta_d), Q, _lib.ptr(ra), _lib.ptr(qfa), sp), "rank")
     _lib.check(lib.qpg_rank512_ties(_lib.ptr(tt_d), Q, _lib.ptr(rt), _lib.ptr(qft), sp), "rank")
+    # per-window phase statistics for the eight-lanes-per-state transition kernel
+    stats = torch.empty((n_seq * 26 * 2 * int(lib.qpg_phase_stats_floats()),), dtype=torch.float32, device=dev)
+    _lib.check(lib.qpg_phase_stats(_lib.ptr(phase_d), n_seq, _lib.ptr(fa_d), _lib.ptr(ft_d), _lib.ptr(stats), sp), "stats")
     outs = []
-    for which in ("old", "direct", "table"):
+    trans_tables = {}
+    for which in ("old", "direct", "table", "table_stats"):
         codes = torch.full((n_clips, n_seg, 30), -7, dtype=torch.int64, device=dev)
         vote = torch.zeros((n_clips, n_seg, 8), dtype=torch.int32, device=dev)
         status = torch.zeros((n_clips,), dtype=torch.int32, device=dev)
@@ -371,13 +379,24 @@ def test_lookup_walk_equals_round1_tail():
             _lib.check(lib.qpg_match_lookup(_lib.ptr(ta_d), _lib.ptr(tt_d), _lib.ptr(ra), _lib.ptr(rt), _lib.ptr(pos_t_d),
                                             _lib.ptr(freq_d), _lib.ptr(code_d), n_seq, _lib.ptr(fa_d), _lib.ptr(ft_d),
                                             _lib.ptr(qfa), _lib.ptr(qft), Q, _lib.ptr(entries), sp), "lookup")
-            trans = torch.empty((Q, 1024), dtype=torch.int16, device=dev) if which == "table" else None
-            _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(code_d), _lib.ptr(phase_d), _lib.ptr(sc_d),
-                                          _lib.ptr(sp_d), n_clips, n_seg, _lib.ptr(trans), _lib.ptr(codes), _lib.ptr(vote),
-                                          _lib.ptr(ph), _lib.ptr(status), sp), "walk")
+            trans = torch.empty((Q, 1024), dtype=torch.int16, device=dev) if which != "direct" else None
+            if which == "table_stats":
+                _lib.check(lib.qpg_match_walk_stats(_lib.ptr(entries), _lib.ptr(code_d), _lib.ptr(phase_d), _lib.ptr(stats),
+                                                    _lib.ptr(sc_d), _lib.ptr(sp_d), n_clips, n_seg, _lib.ptr(trans),
+                                                    _lib.ptr(codes), _lib.ptr(vote), _lib.ptr(ph), _lib.ptr(status), sp),
+                           "walk_stats")
+            else:
+                _lib.check(lib.qpg_match_walk(_lib.ptr(entries), _lib.ptr(code_d), _lib.ptr(phase_d), _lib.ptr(sc_d),
+                                              _lib.ptr(sp_d), n_clips, n_seg, _lib.ptr(trans), _lib.ptr(codes),
+                                              _lib.ptr(vote), _lib.ptr(ph), _lib.ptr(status), sp), "walk")
+            if trans is not None:
+                trans_tables[which] = trans.cpu().numpy()
         torch.cuda.synchronize()
         outs.append((codes.cpu().numpy(), vote.cpu().numpy(), status.cpu().numpy(), ph.cpu().numpy()))
-    (c0, v0, s0, p0), (c1, v1, s1, p1), (c2, v2, s2, p2) = outs
+    (c0, v0, s0, p0), (c1, v1, s1, p1), (c2, v2, s2, p2), (c3, v3, s3, p3) = outs
+    # the transition table from per-window statistics equals the one from the full cosines, state for state
+    assert np.array_equal(trans_tables["table"], trans_tables["table_stats"])
+    assert np.array_equal(c2, c3) and np.array_equal(s2, s3) and np.array_equal(v2, v3) and np.array_equal(p2, p3)
     # direct walk and table walk are the same arithmetic: bit-identical, failed clip included
     assert np.array_equal(c1, c2) and np.array_equal(s1, s2)
     for b in range(n_clips):

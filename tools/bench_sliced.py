@@ -113,8 +113,9 @@ def main():
                                  p.Qt, _lib.ptr(p.entries), SP[0])
 
         def walk_table():
-            lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
-                               p.n_tail, p.n_seg, _lib.ptr(p.trans), _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), SP[0])
+            lib.qpg_match_walk_stats(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.phase_stats),
+                                     _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase), p.n_tail, p.n_seg, _lib.ptr(p.trans),
+                                     _lib.ptr(p.codes), _lib.ptr(p.vote), None, _lib.ptr(p.status), SP[0])
 
         def walk_direct():
             lib.qpg_match_walk(_lib.ptr(p.entries), _lib.ptr(db.code), _lib.ptr(db.phase_amp), _lib.ptr(p.seed_code), _lib.ptr(p.seed_phase),
