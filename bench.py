@@ -65,7 +65,7 @@ def parse():
     p.add_argument("--no-graph", action="store_true", help="plain launches instead of CUDA-graph replay")
     p.add_argument("--scan-priority", type=int, default=0,
                    help="1: the scan of every pipeline lane runs on a high-priority side stream")
-    p.add_argument("--pipeline", type=int, default=4,
+    p.add_argument("--pipeline", type=int, default=8,
                    help="independent steps in flight (each on its own stream with its own buffers); 1 = one stream")
     return p.parse_args()
 
