@@ -756,6 +756,145 @@ __global__ void __launch_bounds__(256, 3)
   else bins_body(tp.t[1], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
 }
 
+// Long bins, CTA-wide: one CTA per (table, start code, four queries), its 256 threads striding the bin's rows, so a
+// 1700-row bin has ~26 independent sacc loads per thread and trip in flight (the warp-per-bin kernel below keeps
+// four: it was bound by bytes in flight, 1.6 ms per 64-step pass of the all-speaker table).  Trip 1: U = min hi
+// (block reduction).  Trip 2: candidates lo <= U into a small shared list.  Then one warp per query writes the
+// record (one candidate) or settles the listed candidates in float64; more than CAND_MAX candidates (degenerate:
+// e.g. an all-zero query ties every row) fall back to re-walking the bin.  sacc is zeroed last.
+constexpr int LQ = 4;            // queries per CTA
+constexpr int CAND_MAX = 32;
+__device__ __forceinline__ void bins_cta_body(const TableParams& T, long long W, long long Wpad, int nq,
+                                              int64_t id_offset, int64_t row_base, int consume,
+                                              unsigned long long* __restrict__ stats) {
+  __shared__ QConst s_qc[LQ];
+  __shared__ unsigned long long s_wmin[LQ][8], s_U[LQ], s_lo1[LQ];
+  __shared__ int s_cnt[LQ], s_cand[LQ][CAND_MAX];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int c = blockIdx.x, q0 = blockIdx.y * LQ;
+  const int ng = min(LQ, nq - q0);
+  if (tid < LQ) {
+    s_qc[tid] = make_qconst(T.q_info[min(q0 + tid, nq - 1)]);
+    s_cnt[tid] = 0;
+    s_lo1[tid] = ~0ull;
+  }
+  const int b0 = T.bin_start[c], b1 = T.bin_start[c + 1];
+  __syncthreads();
+  if (b1 > b0) {
+    // trip 1: U per query
+    unsigned long long um[LQ];
+#pragma unroll
+    for (int g = 0; g < LQ; ++g) um[g] = ~0ull;
+    for (int pos = b0 + tid; pos < b1; pos += 256) {
+      const RowInfo ri = T.row_info[pos];
+      long long v[LQ];
+#pragma unroll
+      for (int g = 0; g < LQ; ++g) v[g] = T.sacc[(size_t)min(q0 + g, nq - 1) * Wpad + pos];
+#pragma unroll
+      for (int g = 0; g < LQ; ++g)
+        um[g] = min(um[g], (unsigned long long)__double_as_longlong(filter_interval(v[g], ri, s_qc[g]).hi));
+    }
+#pragma unroll
+    for (int g = 0; g < LQ; ++g) {
+      const unsigned long long w = warp_min_u64(um[g]);
+      if (lane == 0) s_wmin[g][warp] = w;
+    }
+    __syncthreads();
+    if (tid < LQ) {
+      unsigned long long u = s_wmin[tid][0];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) u = min(u, s_wmin[tid][w]);
+      s_U[tid] = u;
+    }
+    __syncthreads();
+    // trip 2: candidates
+    for (int pos = b0 + tid; pos < b1; pos += 256) {
+      const RowInfo ri = T.row_info[pos];
+      long long v[LQ];
+#pragma unroll
+      for (int g = 0; g < LQ; ++g) v[g] = T.sacc[(size_t)min(q0 + g, nq - 1) * Wpad + pos];
+#pragma unroll
+      for (int g = 0; g < LQ; ++g) {
+        const unsigned long long lo = (unsigned long long)__double_as_longlong(filter_interval(v[g], ri, s_qc[g]).lo);
+        if (g < ng && lo <= s_U[g]) {
+          const int slot = atomicAdd(&s_cnt[g], 1);
+          if (slot < CAND_MAX) s_cand[g][slot] = pos;
+          atomicMin(&s_lo1[g], lo);          // with a single candidate: its lower bound
+        }
+      }
+    }
+    __syncthreads();
+  }
+  // records: warp g settles query q0 + g
+  if (warp < ng) {
+    const int g = warp, qi_ = q0 + g;
+    qpg_bin_t rec;
+    rec.lo = kEmptyDist;
+    rec.hi = kEmptyDist;
+    rec.id = -1;
+    rec.n = 0;
+    rec.flags = 1;                               // empty bins are exact (sentinel)
+    if (b1 > b0) {
+      const int cnt = s_cnt[g];
+      if (cnt == 1) {
+        rec.lo = __longlong_as_double((long long)s_lo1[g]);
+        rec.hi = __longlong_as_double((long long)s_U[g]);
+        rec.id = id_offset + T.order[s_cand[g][0]];
+        rec.n = 1;
+        rec.flags = 0;
+      } else {
+        const float* qrow = T.q + (size_t)qi_ * T.ldq;
+        const double sqq = T.q_info[qi_].sq;
+        BestPair best;
+        best.d = 1e300;
+        best.id = -1;
+        if (cnt <= CAND_MAX) {
+          for (int i = 0; i < cnt; ++i) {
+            const long long w = T.order[s_cand[g][i]];
+            const double d = exact_distance(T.packed, T.NC, w + row_base, qrow, T.D, sqq, T.sqnorm[w + row_base], lane);
+            const long long id = id_offset + w;
+            if (d < best.d || (d == best.d && id < best.id)) {
+              best.d = d;
+              best.id = id;
+            }
+          }
+        } else {                                 // degenerate: walk the bin again, 32 rows at a time
+          const QConst qg = s_qc[g];
+          const unsigned long long U = s_U[g];
+          const long long* sv = T.sacc + (size_t)qi_ * Wpad;
+          for (int base = b0; base < b1; base += 32) {
+            const int pos = base + lane;
+            const bool cand = pos < b1 &&
+                              (unsigned long long)__double_as_longlong(filter_interval(sv[pos], T.row_info[pos], qg).lo) <= U;
+            const unsigned m = __ballot_sync(0xffffffffu, cand);
+            if (m) best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m, base, qrow, sqq, id_offset, row_base, lane, best);
+          }
+        }
+        rec.lo = best.d;
+        rec.hi = best.d;
+        rec.id = best.id;
+        rec.n = cnt;
+        rec.flags = 1;
+        if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)cnt);
+      }
+    }
+    if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
+  }
+  if (consume) {
+    __syncthreads();                             // the degenerate path above still reads sacc
+    const long long end = c == KB - 1 ? W : b1;  // rows with a label outside [0, 512) belong to no bin
+    for (long long pos = b0 + tid; pos < end; pos += 256)
+      for (int g = 0; g < ng; ++g) T.sacc[(size_t)(q0 + g) * Wpad + pos] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(256, 3)
+    sliced_bins_cta_kernel(const __grid_constant__ TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset,
+                           int64_t row_base, int consume, unsigned long long* __restrict__ stats) {
+  if (blockIdx.z == 0) bins_cta_body(tp.t[0], W, Wpad, nq, id_offset, row_base, consume, stats);
+  else bins_cta_body(tp.t[1], W, Wpad, nq, id_offset, row_base, consume, stats);
+}
+
 // Long bins (all-speaker tables and the synthetic sweeps: hundreds to thousands of rows per start code): the first
 // version of the kernel, one warp per (table, start code, four queries) with the four sacc loads of a lane in flight
 // together on both trips over the bin - the one-trip kernel above is sequential per query on such bins.
@@ -1241,6 +1380,10 @@ extern "C" int qpg_sliced_bins(const qpg_sliced_table_t* tabs, int n_tabs, int64
     const dim3 grid(KB / 8, (unsigned)((nq + BG - 1) / BG), (unsigned)n_tabs);    // CTA = 8 start codes x 8 queries
     sliced_bins_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
                                                                reinterpret_cast<unsigned long long*>(stats));
+  } else if (W >= 128 * KB) {                  // hundreds of rows per start code: a CTA per bin
+    const dim3 grid(KB, (unsigned)((nq + LQ - 1) / LQ), (unsigned)n_tabs);
+    sliced_bins_cta_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(tp, W, Wpad, nq, id_offset, row_base, consume,
+                                                                   reinterpret_cast<unsigned long long*>(stats));
   } else {
     const long long warps = (long long)((nq + BGL - 1) / BGL) * KB;
     const dim3 grid((unsigned)((warps * 32 + 255) / 256), (unsigned)n_tabs);

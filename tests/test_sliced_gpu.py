@@ -212,7 +212,7 @@ def _tables_sliced(rows, labels, q, id_offset=0, column_scaling=True):
 
 @pytest.mark.parametrize("W,D,Q,nbins,special", [(1000, 384, 3, 300, True), (5000, 512, 16, 512, False),
                                                  (2048, 6144, 5, 64, True), (40, 130, 2, 512, False),
-                                                 (26000, 384, 48, 512, True)])
+                                                 (26000, 384, 48, 512, True), (70000, 64, 9, 512, True)])
 def test_sliced_tables_vs_float64(W, D, Q, nbins, special):
     """ids, empty bins and rank transform identical to the float64 evaluation; distances within 2e-7 (exact where a
     decision was needed)"""
@@ -230,6 +230,8 @@ def test_sliced_tables_vs_float64(W, D, Q, nbins, special):
         rows[21] = rows[20] + np.float32(3e-6) * rng.standard_normal(D).astype(np.float32)
         labels[21] = labels[20]
         q[1] = rows[20]
+        if Q > 8:
+            q[8] = 0.0                                        # all-zero query: every row of a bin ties (degenerate path)
         labels[30] = 999                                      # ignored row
     table, ranks, qf, stats, _ = _tables_sliced(rows, labels, q, id_offset=26 * 7)
     d = sm.f64_distances(rows, q)
