@@ -616,21 +616,31 @@ __device__ __forceinline__ void bins_body(const TableParams& T, QConst* s_qc, lo
   const int n = b1 - b0;
   const int ng = min(BG, nq - q0);
   const unsigned long long kInf = ~0ull;
-  if (n <= 32) {
-    // ---- the whole bin in one trip: lane = row.  The BG accumulators of a row go global -> shared by cp.async
-    // (eight copies in flight per lane without holding 16 registers), then one query at a time ----
-    const bool valid = lane < n;
-    const int pos = b0 + lane;
-    RowInfo ri;
-    ri.r1 = ri.r2 = 0.0;
-    long long* my_v = s_v + (warp * BG) * 32 + lane;
-    if (valid) {
+  if (n <= 64) {
+    // ---- the whole bin in one trip: lane = rows `lane` and `lane + 32`.  The BG accumulators of a row go global ->
+    // shared by cp.async (sixteen copies in flight per lane without holding 32 registers), then one query at a time.
+    // (Bins of 33-64 rows used to take the sequential path below: a tenth of the bins at 26 windows per sequence,
+    // and 17 % of the kernel's stall samples - each of those warps ran ~30 dependent round trips.)
+    const bool valid0 = lane < n, valid1 = lane + 32 < n;
+    const int pos0 = b0 + lane, pos1 = pos0 + 32;
+    RowInfo ri0, ri1;
+    ri0.r1 = ri0.r2 = ri1.r1 = ri1.r2 = 0.0;
+    long long* my_v = s_v + (warp * BG) * 64 + lane;
+    if (valid0) {
 #pragma unroll
       for (int g = 0; g < BG; ++g) {
-        const long long* src = T.sacc + (size_t)min(q0 + g, nq - 1) * Wpad + pos;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(my_v + g * 32)), "l"(src) : "memory");
+        const long long* src = T.sacc + (size_t)min(q0 + g, nq - 1) * Wpad + pos0;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(my_v + g * 64)), "l"(src) : "memory");
       }
-      ri = T.row_info[pos];
+      ri0 = T.row_info[pos0];
+    }
+    if (valid1) {
+#pragma unroll
+      for (int g = 0; g < BG; ++g) {
+        const long long* src = T.sacc + (size_t)min(q0 + g, nq - 1) * Wpad + pos1;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(my_v + g * 64 + 32)), "l"(src) : "memory");
+      }
+      ri1 = T.row_info[pos1];
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
@@ -644,33 +654,43 @@ __device__ __forceinline__ void bins_body(const TableParams& T, QConst* s_qc, lo
       rec.n = 0;
       rec.flags = 1;                             // empty bins are exact (sentinel)
       if (n > 0) {
-        Interval iv;
-        iv.lo = iv.hi = 0.0;
-        if (valid) {
-          iv = filter_interval(my_v[g * 32], ri, s_qc[g]);
-          if (consume) T.sacc[(size_t)qi_ * Wpad + pos] = 0;
+        Interval iv0, iv1;
+        iv0.lo = iv0.hi = iv1.lo = iv1.hi = 0.0;
+        if (valid0) {
+          iv0 = filter_interval(my_v[g * 64], ri0, s_qc[g]);
+          if (consume) T.sacc[(size_t)qi_ * Wpad + pos0] = 0;
+        }
+        if (valid1) {
+          iv1 = filter_interval(my_v[g * 64 + 32], ri1, s_qc[g]);
+          if (consume) T.sacc[(size_t)qi_ * Wpad + pos1] = 0;
         }
         // non-negative doubles order like their bit patterns
-        const unsigned long long U = warp_min_u64(valid ? (unsigned long long)__double_as_longlong(iv.hi) : kInf);
-        const bool cand = valid && (unsigned long long)__double_as_longlong(iv.lo) <= U;
-        const unsigned m = __ballot_sync(0xffffffffu, cand);
-        if (__popc(m) == 1) {
-          const int src = __ffs(m) - 1;
-          rec.lo = __shfl_sync(0xffffffffu, iv.lo, src);
+        const unsigned long long h0 = valid0 ? (unsigned long long)__double_as_longlong(iv0.hi) : kInf;
+        const unsigned long long h1 = valid1 ? (unsigned long long)__double_as_longlong(iv1.hi) : kInf;
+        const unsigned long long U = warp_min_u64(h0 < h1 ? h0 : h1);
+        const bool cand0 = valid0 && (unsigned long long)__double_as_longlong(iv0.lo) <= U;
+        const bool cand1 = valid1 && (unsigned long long)__double_as_longlong(iv1.lo) <= U;
+        const unsigned m0 = __ballot_sync(0xffffffffu, cand0), m1 = __ballot_sync(0xffffffffu, cand1);
+        const int cnt = __popc(m0) + __popc(m1);
+        if (cnt == 1) {
+          const int src = __ffs(m0 | m1) - 1;
+          rec.lo = __shfl_sync(0xffffffffu, m0 ? iv0.lo : iv1.lo, src);
           rec.hi = __longlong_as_double((long long)U);
-          rec.id = id_offset + T.order[b0 + src];
+          rec.id = id_offset + T.order[b0 + src + (m0 ? 0 : 32)];
           rec.n = 1;
           rec.flags = 0;
         } else {
           BestPair best;
           best.d = 1e300;
           best.id = -1;
-          best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m, b0, T.q + (size_t)qi_ * T.ldq, T.q_info[qi_].sq,
-                             id_offset, row_base, lane, best);
+          const float* qrow = T.q + (size_t)qi_ * T.ldq;
+          const double sqq = T.q_info[qi_].sq;
+          if (m0) best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m0, b0, qrow, sqq, id_offset, row_base, lane, best);
+          if (m1) best = bins_verify(T.packed, T.sqnorm, T.order, T.NC, T.D, m1, b0 + 32, qrow, sqq, id_offset, row_base, lane, best);
           rec.lo = best.d;
           rec.hi = best.d;
           rec.id = best.id;
-          rec.n = __popc(m);                     // how many rows were re-evaluated (diagnostics)
+          rec.n = cnt;                           // how many rows were re-evaluated (diagnostics)
           rec.flags = 1;                         // exact
           if (lane == 0 && stats) atomicAdd(&stats[0], (unsigned long long)rec.n);
         }
@@ -678,7 +698,7 @@ __device__ __forceinline__ void bins_body(const TableParams& T, QConst* s_qc, lo
       if (lane == 0) T.bins[(size_t)qi_ * T.bins_qstride + c] = rec;
     }
   } else {
-    // ---- long bins (all-speaker tables: ~1700 rows per code): two trips per query, 32 rows at a time ----
+    // ---- more than 64 rows in a bin of a small table (rare): two trips per query, 32 rows at a time ----
 #pragma unroll 1
     for (int g = 0; g < ng; ++g) {
       const int qi_ = q0 + g;
@@ -751,7 +771,7 @@ __global__ void __launch_bounds__(256, 3)
     sliced_bins_kernel(const __grid_constant__ TablePair tp, long long W, long long Wpad, int nq, int64_t id_offset,
                        int64_t row_base, int consume, unsigned long long* __restrict__ stats) {
   __shared__ QConst s_qc[BG];
-  __shared__ long long s_v[8 * BG * 32];         // [warp][query][lane] accumulators of the warp's bin
+  __shared__ long long s_v[8 * BG * 64];         // [warp][query][row] accumulators of the warp's bin (32 KiB)
   if (blockIdx.z == 0) bins_body(tp.t[0], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
   else bins_body(tp.t[1], s_qc, s_v, W, Wpad, nq, id_offset, row_base, consume, stats);
 }
