@@ -568,8 +568,8 @@ struct TablePair {
 // work per round trip and residency: the BG = 8 sacc loads of a lane are issued together, a bin of up to 32 rows
 // (nearly all of them at 26 windows per sequence) is settled from registers in ONE trip over its rows, the
 // per-query constants sit in shared memory, and the 64-bit minimum over the warp is two REDUX instead of ten
-// shuffles.  9.3 M warp instructions instead of 13.7 M (ncu); 26 us alone (first version 28.8), and 5 us less per
-// step when it runs in the shadow of another lane's scan (80 registers instead of 128).
+// shuffles.  9.3 M warp instructions instead of 13.7 M (ncu), 80 registers instead of 128; 17 us alone (first version
+// 28.8) once the 33-64-row bins took the one-trip path too.
 constexpr int BG = 8;
 
 __device__ __forceinline__ unsigned long long warp_min_u64(unsigned long long v) {
