@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256, 6)
 // only), so the pos_rank_t[c][last] loads stay coalesced.  The arg-min rule is match_lookup_kernel's: integer keys,
 // float64 comparison with NumPy's operation order on equal keys, the lower code on exact ties (flagged).  Steps
 // with empty bins take the full loop in code order (sentinel rule, see match_lookup_kernel).
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
     match_lookup_pruned_kernel(const Pair* __restrict__ aud_table, const Pair* __restrict__ txt_table,
                                const int32_t* __restrict__ aud_rank, const int32_t* __restrict__ txt_rank,
                                const int16_t* __restrict__ pos_rank_t, const int32_t* __restrict__ freq_rank,
@@ -219,10 +219,15 @@ __global__ void __launch_bounds__(256)
   __shared__ int s_fr[KB];
   __shared__ short s_inv[2][KB];                // code by rank
   __shared__ int s_ne[2];
+  __shared__ long long s_w[256];                // the text half of the entry, handed to the audio thread
+  __shared__ int s_half[256];                   // nl | nls << 9 | frame << 18 | flag << 27
   const int q = blockIdx.x, tid = threadIdx.x;
-  const int last = blockIdx.y * 256 + tid;
-  int ne_a = 0, ne_t = 0;
-  for (int c = tid; c < KB; c += 256) {
+  // threads 0-255 search the audio table, 256-511 the text table, for the same 256 values of `last`: the two
+  // searches are independent chains of ~9 dependent gather batches each, so they run side by side
+  const int x = tid >> 8, lt = tid & 255;
+  const int last = blockIdx.y * 256 + lt;
+  {
+    const int c = tid;                          // 512 threads stage one code each
     const int fr = freq_rank[c];
     const int ra = aud_rank[(size_t)q * KB + c], rt = txt_rank[(size_t)q * KB + c];
     const long long ida = (long long)aud_table[(size_t)q * KB + c].id, idt = (long long)txt_table[(size_t)q * KB + c].id;
@@ -231,101 +236,107 @@ __global__ void __launch_bounds__(256)
     s_key[1][c] = (20 * rt + fr) | (idt < 0 ? EMPTY : 0);
     s_inv[0][ra & (KB - 1)] = (short)c;
     s_inv[1][rt & (KB - 1)] = (short)c;
-    ne_a += ida >= 0;
-    ne_t += idt >= 0;
-  }
-  const int na1 = __syncthreads_count(ne_a >= 1), na2 = __syncthreads_count(ne_a >= 2);
-  const int nt1 = __syncthreads_count(ne_t >= 1), nt2 = __syncthreads_count(ne_t >= 2);
-  if (tid == 0) {
-    s_ne[0] = na1 + na2;
-    s_ne[1] = nt1 + nt2;
+    const int na = __syncthreads_count(ida >= 0), nt = __syncthreads_count(idt >= 0);
+    if (tid == 0) {
+      s_ne[0] = na;
+      s_ne[1] = nt;
+    }
   }
   __syncthreads();
-  auto f64_value = [&](int pos, int c, int x) {
+  auto f64_value = [&](int pos, int c) {
     const int fr = s_fr[c];
     const int rk = ((s_key[x][c] & ~EMPTY) - fr) / 20;
     return __dadd_rn(__dadd_rn((double)pos, __dmul_rn((double)fr, 0.05)), (double)rk);
   };
-  int best[2] = {0x7fffffff, 0x7fffffff}, arg[2] = {0, 0}, bpos[2] = {0, 0}, tie[2] = {0, 0};
-  int best_ne[2] = {0x7fffffff, 0x7fffffff};       // best key over non-empty bins
-  int lb_e[2] = {0x3fffffff, 0x3fffffff};          // min over empty bins of 20*pos + freq
-  auto offer = [&](int x, int key, int c, int pos) {       // any visiting order: the lower code stays on exact ties
-    if (key < best[x]) {
-      best[x] = key;
-      arg[x] = c;
-      bpos[x] = pos;
-      tie[x] = 0;
-    } else if (key == best[x]) {
-      const double vb = f64_value(bpos[x], arg[x], x), vc = f64_value(pos, c, x);
+  int best = 0x7fffffff, arg = 0, bpos = 0, tie = 0;
+  int best_ne = 0x7fffffff;                        // best key over non-empty bins
+  int lb_e = 0x3fffffff;                           // min over empty bins of 20*pos + freq
+  auto offer = [&](int key, int c, int pos) {      // any visiting order: the lower code stays on exact ties
+    if (key < best) {
+      best = key;
+      arg = c;
+      bpos = pos;
+      tie = 0;
+    } else if (key == best) {
+      const double vb = f64_value(bpos, arg), vc = f64_value(pos, c);
       if (vc < vb) {
-        arg[x] = c;
-        bpos[x] = pos;
-        tie[x] = 0;
+        arg = c;
+        bpos = pos;
+        tie = 0;
       } else if (vc == vb) {
-        tie[x] = 1;
-        if (c < arg[x]) {
-          arg[x] = c;
-          bpos[x] = pos;
+        tie = 1;
+        if (c < arg) {
+          arg = c;
+          bpos = pos;
         }
       }
     }
   };
-  const bool any_empty = s_ne[0] < KB || s_ne[1] < KB;          // block uniform; false for any sizeable database
-  if (!any_empty) {
+  if (s_ne[x] == KB) {                             // warp uniform (x is): no empty bin in this table
+    for (int r0 = 0; r0 < KB && 20 * r0 <= best; r0 += 8) {       // eight loads in flight per round trip
+      int cc[8], pr[8];
 #pragma unroll
-    for (int x = 0; x < 2; ++x) {
-      for (int r0 = 0; r0 < KB && 20 * r0 <= best[x]; r0 += 8) {       // eight loads in flight per round trip
-        int cc[8], pr[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          cc[i] = s_inv[x][r0 + i];
-          pr[i] = (int)pos_rank_t[(size_t)cc[i] * KB + last];
-        }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) offer(x, 20 * pr[i] + s_key[x][cc[i]], cc[i], pr[i]);
+      for (int i = 0; i < 8; ++i) {
+        cc[i] = s_inv[x][r0 + i];
+        pr[i] = (int)pos_rank_t[(size_t)cc[i] * KB + last];
       }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) offer(20 * pr[i] + s_key[x][cc[i]], cc[i], pr[i]);
     }
-  } else {
+  } else {                                         // empty bins: every code, in code order (sentinel rule)
     for (int c0 = 0; c0 < KB; c0 += 8) {
       int pr[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) pr[i] = (int)pos_rank_t[(size_t)(c0 + i) * KB + last];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int c = c0 + i, p20 = 20 * pr[i], fr = s_fr[c];
-#pragma unroll
-        for (int x = 0; x < 2; ++x) {
-          const int sk = s_key[x][c];
-          const int key = p20 + (sk & ~EMPTY);
-          offer(x, key, c, pr[i]);
-          if (sk & EMPTY) lb_e[x] = min(lb_e[x], p20 + fr);
-          else best_ne[x] = min(best_ne[x], key);
-        }
+        const int c = c0 + i, p20 = 20 * pr[i], sk = s_key[x][c];
+        const int key = p20 + (sk & ~EMPTY);
+        offer(key, c, pr[i]);
+        if (sk & EMPTY) lb_e = min(lb_e, p20 + s_fr[c]);
+        else best_ne = min(best_ne, key);
       }
     }
   }
-  Entry e;
-  e.flags = ((qflags_a && qflags_a[q]) || (qflags_t && qflags_t[q])) ? 1 : 0;
-#pragma unroll
-  for (int x = 0; x < 2; ++x) {
-    if (tie[x]) e.flags |= 1;                      // a true tie at the arg-min: NumPy's order is platform defined
+  // this thread's half of the entry
+  int flag = tie;                                  // a true tie at the arg-min: NumPy's order is platform defined
+  {
+    // empty bins all hold the sentinel 1e3, their mutual rank order is NumPy's business: the lowest rank any of
+    // them can get is the number of non-empty bins.  If that could reach the best non-empty key, say so.
     const int ne = s_ne[x];
-    if (ne < KB && lb_e[x] + 20 * ne <= best_ne[x]) e.flags |= 1;     // an empty bin could win (sentinel ties)
-    const Pair* table = x == 0 ? aud_table : txt_table;
-    const long long w = (long long)table[(size_t)q * KB + arg[x]].id;
-    e.w[x] = -1;
-    e.nl[x] = e.nls[x] = 0;
-    e.frame[x] = 0;
-    if (w >= 0 && w < n_seq * WIN) {
-      const long long j = w / WIN;
-      const int m = (int)(w - j * WIN);
-      e.w[x] = w;
-      e.nl[x] = (short)code[(size_t)j * NCODE + m + 3];
-      e.nls[x] = (short)code[(size_t)j * NCODE + m + 1];
-      e.frame[x] = (short)(x == 0 ? aud_frame : txt_frame)[m];
-    }
+    if (ne < KB && lb_e + 20 * ne <= best_ne) flag = 1;
   }
-  entries[(size_t)q * KB + last] = e;
+  const Pair* table = x == 0 ? aud_table : txt_table;
+  const long long w = (long long)table[(size_t)q * KB + arg].id;
+  long long ew = -1;
+  int nl = 0, nls = 0, frame = 0;
+  if (w >= 0 && w < n_seq * WIN) {
+    const long long j = w / WIN;
+    const int m = (int)(w - j * WIN);
+    ew = w;
+    nl = code[(size_t)j * NCODE + m + 3];
+    nls = code[(size_t)j * NCODE + m + 1];
+    frame = (x == 0 ? aud_frame : txt_frame)[m];
+  }
+  if (x == 1) {
+    s_w[lt] = ew;
+    s_half[lt] = (nl & 511) | ((nls & 511) << 9) | ((frame & 511) << 18) | (flag << 27);
+  }
+  __syncthreads();
+  if (x == 0) {
+    const int h = s_half[lt];
+    Entry e;
+    e.flags = (((qflags_a && qflags_a[q]) || (qflags_t && qflags_t[q])) ? 1 : 0) | flag | ((h >> 27) & 1);
+    e.w[0] = ew;
+    e.w[1] = s_w[lt];
+    e.nl[0] = (short)nl;
+    e.nl[1] = (short)(h & 511);
+    e.nls[0] = (short)nls;
+    e.nls[1] = (short)((h >> 9) & 511);
+    e.frame[0] = (short)frame;
+    e.frame[1] = (short)((h >> 18) & 511);
+    entries[(size_t)q * KB + last] = e;
+  }
 }
 
 __device__ __forceinline__ Entry load_entry(const Entry* p) {
@@ -774,7 +785,7 @@ extern "C" int qpg_match_lookup(const qpg_pair_t* aud_table, const qpg_pair_t* t
                     txt_frame && entries,
                 "null pointer");
   QPG_CHECK_ARG((reinterpret_cast<uintptr_t>(entries) & 15) == 0, "entries must be 16-byte aligned");
-  match_lookup_pruned_kernel<<<dim3((unsigned)Q, 2), 256, 0, (cudaStream_t)stream>>>(
+  match_lookup_pruned_kernel<<<dim3((unsigned)Q, 2), 512, 0, (cudaStream_t)stream>>>(
       reinterpret_cast<const Pair*>(aud_table), reinterpret_cast<const Pair*>(txt_table), aud_rank, txt_rank, pos_rank_t,
       freq_rank, code, n_seq, aud_frame, txt_frame, qflags_a, qflags_t, reinterpret_cast<Entry*>(entries));
   QPG_LAUNCH_CHECK();
