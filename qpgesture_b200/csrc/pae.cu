@@ -87,23 +87,28 @@ pae_sliding_conv1_kernel(const float* __restrict__ vel, const float* __restrict_
 }
 
 // ---- plain batched convolution, float32 FFMA (second conv of pose2phase; all four convs of Model.forward) ------
+// One CTA = 8 output channels x 256 positions x TWO windows: the staged weights (the larger operand) serve both
+// windows, which halves the weight staging and the shared-memory reads per multiply-add.
 constexpr int CONV_OG = 8;       // output channels per CTA
 constexpr int CONV_CC = 15;      // input channels staged per chunk
 constexpr int CONV_TT = 256;     // output positions per CTA
+constexpr int CONV_NW = 2;       // windows per CTA
 
 __global__ void __launch_bounds__(256, 1)
 pae_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ scale,
-                  const float* __restrict__ shift, int Ci, int Lin, int Co, int K, int pad, int Lo, int act,
+                  const float* __restrict__ shift, int B, int Ci, int Lin, int Co, int K, int pad, int Lo, int act,
                   float* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* ws = reinterpret_cast<float*>(smem_raw);                 // [CONV_OG][CONV_CC][K]
-  float* xs = ws + CONV_OG * CONV_CC * K;                         // [CONV_CC][CONV_TT + K - 1]
+  float* xs = ws + CONV_OG * CONV_CC * K;                         // [CONV_NW][CONV_CC][CONV_TT + K - 1]
   const int xw = CONV_TT + K - 1;
-  const int t0 = blockIdx.x * CONV_TT, o0 = blockIdx.y * CONV_OG, b = blockIdx.z;
+  const int t0 = blockIdx.x * CONV_TT, o0 = blockIdx.y * CONV_OG, b0 = blockIdx.z * CONV_NW;
   const int t = threadIdx.x;
-  float acc[CONV_OG];
+  float acc[CONV_NW][CONV_OG];
 #pragma unroll
-  for (int o = 0; o < CONV_OG; ++o) acc[o] = 0.f;
+  for (int n = 0; n < CONV_NW; ++n)
+#pragma unroll
+    for (int o = 0; o < CONV_OG; ++o) acc[n][o] = 0.f;
   for (int c0 = 0; c0 < Ci; c0 += CONV_CC) {
     const int cc = min(CONV_CC, Ci - c0);
     for (int idx = threadIdx.x; idx < CONV_OG * cc * K; idx += blockDim.x) {
@@ -111,23 +116,31 @@ pae_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
       const int c = r / K, kk = r - c * K;
       ws[(o * CONV_CC + c) * K + kk] = (o0 + o < Co) ? w[((size_t)(o0 + o) * Ci + c0 + c) * K + kk] : 0.f;
     }
-    for (int idx = threadIdx.x; idx < cc * xw; idx += blockDim.x) {
-      const int c = idx / xw, j = idx - c * xw;
+    for (int idx = threadIdx.x; idx < CONV_NW * cc * xw; idx += blockDim.x) {
+      const int n = idx / (cc * xw), r = idx - n * (cc * xw);
+      const int c = r / xw, j = r - c * xw;
       const int pos = t0 + j - pad;
-      xs[c * xw + j] = (pos >= 0 && pos < Lin) ? x[((size_t)b * Ci + c0 + c) * Lin + pos] : 0.f;
+      xs[(n * CONV_CC + c) * xw + j] =
+          (b0 + n < B && pos >= 0 && pos < Lin) ? x[((size_t)(b0 + n) * Ci + c0 + c) * Lin + pos] : 0.f;
     }
     __syncthreads();
     for (int c = 0; c < cc; ++c) {
-      const float* xc = xs + c * xw + t;
+      const float* xc0 = xs + c * xw + t;
+      const float* xc1 = xs + (CONV_CC + c) * xw + t;
       for (int kk = 0; kk < K; kk += 4) {
-        const float x0 = xc[kk], x1 = xc[kk + 1], x2 = xc[kk + 2], x3 = xc[kk + 3];
+        const float a0 = xc0[kk], a1 = xc0[kk + 1], a2 = xc0[kk + 2], a3 = xc0[kk + 3];
+        const float b0v = xc1[kk], b1v = xc1[kk + 1], b2v = xc1[kk + 2], b3v = xc1[kk + 3];
 #pragma unroll
         for (int o = 0; o < CONV_OG; ++o) {
           const float4 wv = *reinterpret_cast<const float4*>(ws + (o * CONV_CC + c) * K + kk);
-          acc[o] = fmaf(wv.x, x0, acc[o]);
-          acc[o] = fmaf(wv.y, x1, acc[o]);
-          acc[o] = fmaf(wv.z, x2, acc[o]);
-          acc[o] = fmaf(wv.w, x3, acc[o]);
+          acc[0][o] = fmaf(wv.x, a0, acc[0][o]);
+          acc[0][o] = fmaf(wv.y, a1, acc[0][o]);
+          acc[0][o] = fmaf(wv.z, a2, acc[0][o]);
+          acc[0][o] = fmaf(wv.w, a3, acc[0][o]);
+          acc[1][o] = fmaf(wv.x, b0v, acc[1][o]);
+          acc[1][o] = fmaf(wv.y, b1v, acc[1][o]);
+          acc[1][o] = fmaf(wv.z, b2v, acc[1][o]);
+          acc[1][o] = fmaf(wv.w, b3v, acc[1][o]);
         }
       }
     }
@@ -135,11 +148,15 @@ pae_conv1d_kernel(const float* __restrict__ x, const float* __restrict__ w, cons
   }
   if (t0 + t < Lo) {
 #pragma unroll
-    for (int o = 0; o < CONV_OG; ++o)
-      if (o0 + o < Co) {
-        float v = fmaf(scale[o0 + o], acc[o], shift[o0 + o]);
-        if (act) v = tanhf(v);
-        out[((size_t)b * Co + o0 + o) * Lo + t0 + t] = v;
+    for (int n = 0; n < CONV_NW; ++n)
+      if (b0 + n < B) {
+#pragma unroll
+        for (int o = 0; o < CONV_OG; ++o)
+          if (o0 + o < Co) {
+            float v = fmaf(scale[o0 + o], acc[n][o], shift[o0 + o]);
+            if (act) v = tanhf(v);
+            out[((size_t)(b0 + n) * Co + o0 + o) * Lo + t0 + t] = v;
+          }
       }
   }
 }
@@ -247,12 +264,12 @@ extern "C" int qpg_pae_conv1d(const float* x, const float* w, const float* scale
   QPG_CHECK_ARG(K >= 4 && K % 4 == 0 && K <= 256, "kernel width must be a multiple of 4, at most 256");
   const int Lo = Lin + 2 * pad - K + 1;
   QPG_CHECK_ARG(Lo >= 1, "kernel wider than the padded input");
-  QPG_CHECK_ARG(B <= 65535, "at most 65535 windows per call");
+  QPG_CHECK_ARG(B <= 65535 * CONV_NW, "at most 131070 windows per call");
   if (B <= 0) return QPG_OK;
-  const size_t smem = sizeof(float) * ((size_t)CONV_OG * CONV_CC * K + (size_t)CONV_CC * (CONV_TT + K - 1));
+  const size_t smem = sizeof(float) * ((size_t)CONV_OG * CONV_CC * K + (size_t)CONV_NW * CONV_CC * (CONV_TT + K - 1));
   QPG_CUDA(cudaFuncSetAttribute(pae_conv1d_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  dim3 grid((Lo + CONV_TT - 1) / CONV_TT, (Co + CONV_OG - 1) / CONV_OG, B);
-  pae_conv1d_kernel<<<grid, 256, smem, stream>>>(x, w, scale, shift, Ci, Lin, Co, K, pad, Lo, act, out);
+  dim3 grid((Lo + CONV_TT - 1) / CONV_TT, (Co + CONV_OG - 1) / CONV_OG, (B + CONV_NW - 1) / CONV_NW);
+  pae_conv1d_kernel<<<grid, 256, smem, stream>>>(x, w, scale, shift, B, Ci, Lin, Co, K, pad, Lo, act, out);
   QPG_LAUNCH_CHECK();
   return QPG_OK;
 }
