@@ -440,6 +440,19 @@ int qpg_legacy_gather(const double* feat, const double* motion, int n_seq, int n
                       const int32_t* desired_k, int j0, int out_frames, int step_idx, int n_steps, double* pred,
                       double* next_pose, int32_t* chosen_log, int32_t* status, void* stream);
 
+/* ---------------- post-decode pose processing: the numeric half of make_bvh_GENEA2020_BT ----------------
+ * (process/process_bvh.py:57-77).  qpg_savgol15_f64: Savitzky-Golay filter (window 15, order 2, scipy mode "interp")
+ * of every column of x [T, C] float32 over time -> out [T, C] float64.  coef [15]: scipy.signal.savgol_coeffs(15, 2);
+ * edge_first / edge_last [7, 15]: rows that evaluate the quadratic fitted to the first / last 15 frames at the
+ * first / last 7 frames (built by the host shim).  T >= 15.
+ * qpg_rotmat_to_euler_zxy: mats [N, 9] row-major 3x3 -> euler_deg [N, 3] = Rotation.from_matrix(m).as_euler('ZXY',
+ * degrees=True): matrices that are not orthogonal (scipy's isclose test) are replaced by their orthogonal polar
+ * factor U V^T first.  flags [N] (nullable): bit 0 = non-positive determinant (scipy raises ValueError), bit 1 =
+ * gimbal lock (third angle set to zero, as scipy does with a warning). */
+int qpg_savgol15_f64(const float* x, int T, int C, const double* coef, const double* edge_first, const double* edge_last,
+                     double* out, void* stream);
+int qpg_rotmat_to_euler_zxy(const double* mats, int64_t N, double* euler_deg, int32_t* flags, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

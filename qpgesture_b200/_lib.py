@@ -106,6 +106,8 @@ SIGNATURES = {
     "qpg_pae_sliding_conv1": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _INT, _P, _P]),
     "qpg_pae_conv1d": (_INT, [_P, _P, _P, _P, _INT, _INT, _INT, _INT, _INT, _INT, _INT, _P, _P]),
     "qpg_pae_params": (_INT, [_P, _P, _P, _P, _P, C.c_float, _INT, _INT, _INT, _P, _P]),
+    "qpg_savgol15_f64": (_INT, [_P, _INT, _INT, _P, _P, _P, _P, _P]),
+    "qpg_rotmat_to_euler_zxy": (_INT, [_P, _I64, _P, _P, _P]),
     "qpg_legacy_cand_bytes": (C.c_size_t, []),
     "qpg_legacy_candidates": (_INT, [_P, _P] + [_INT] * 8 + [_P, _INT, _P, _P, _P, _P, _P]),
     "qpg_legacy_pick": (_INT, [_P, _P, _P, _INT, _INT, _P, _P, _P, _P, _P]),
