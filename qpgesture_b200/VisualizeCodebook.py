@@ -85,17 +85,25 @@ def cal_distance(args, model_path, save_path, prefix, normalize=True, model=None
 
 def visualizeCodeAndWrite(code_path=None, save_path="./Speech2GestureMatching/output/", prefix=None,
                           pipeline_path="../data/data_pipe_60_rotation.sav", generateGT=True, code_source=None, vis=True,
-                          *, config=None, model_path=None, model=None):
-    """Inference half of VisualizeCodebook.py:333-370 (code file -> poses) with the reference's positional
-    arguments; the files go to os.path.join(save_path, prefix) like the reference's (:342), which is where its BVH
-    step (not built: needs the unshipped data_pipe_60_rotation.sav) looks for them.  `config` (keyword, the
-    reference reads a module global) carries VQVAE / data_mean / data_std / VQVAE_model_path."""
+                          *, config=None, model_path=None, model=None, bvh=True):
+    """Inference half of VisualizeCodebook.py:333-370 (code file -> poses -> Euler angles / BVH) with the reference's
+    positional arguments; the files go to os.path.join(save_path, prefix) like the reference's (:342).  The BVH step
+    (:361, `make_bvh_GENEA2020_BT(..., smoothing=False, pipeline_path=...)`) runs its numeric half on the device
+    (qpgesture_b200.process_bvh) and writes `<prefix>_generated.bvh` when pymo and the fitted pipeline are available,
+    else `<prefix>_generated_euler.npy`; `bvh=False` stops after the poses.  The ground-truth branch (generateGT:
+    parsing a BVH file with pymo, :346-355) and the video rendering (vis, :363-370) are not built.  `config`
+    (keyword, the reference reads a module global) carries VQVAE / data_mean / data_std / VQVAE_model_path."""
     assert config is not None, "pass config= (the reference reads a module-level global)"
     if code_source is None:
         code_source = np.load(code_path)["knn_pred"]                     # :357
     model_path = model_path or getattr(config, "VQVAE_model_path", None)
     save_path = os.path.join(save_path, prefix)                          # :342
-    return visualize_code(config, model_path, save_path, prefix, code_source, model=model)
+    out_poses, out_code = visualize_code(config, model_path, save_path, prefix, code_source, model=model)
+    if bvh:
+        from .process_bvh import make_bvh_GENEA2020_BT
+        make_bvh_GENEA2020_BT(save_path, prefix, out_poses, smoothing=False, pipeline_path=pipeline_path,
+                              device=getattr(model, "device", None))          # :361
+    return out_poses, out_code
 
 
 def main(argv=None):

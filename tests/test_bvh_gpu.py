@@ -64,3 +64,24 @@ def test_errors_and_fallback_file(tmp_path):
         out = make_bvh_GENEA2020_BT(str(tmp_path), "clip", poses, smoothing=True, pipeline_path=str(tmp_path / "none.sav"),
                                     device="cuda:0")
     assert out.endswith("_generated_euler.npy") and np.load(out).shape == (20, 45)
+
+
+def test_visualize_code_and_write_runs_the_bvh_step(tmp_path, monkeypatch):
+    """VisualizeCodebook.visualizeCodeAndWrite (:333-361): decoded poses -> make_bvh_GENEA2020_BT(smoothing=False);
+    without pymo / the fitted pipeline the Euler angles land next to where the BVH file would go."""
+    import warnings
+    from types import SimpleNamespace
+    from oracle import bvh_np
+    from qpgesture_b200 import VisualizeCodebook as VC
+
+    poses = smooth_poses(24, 15, 0.03)
+    monkeypatch.setattr(VC, "visualize_code", lambda *a, **k: (poses, np.zeros((1, 3), dtype=np.int64)))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out_poses, _ = VC.visualizeCodeAndWrite(code_source=np.zeros((1, 3), dtype=np.int64), save_path=str(tmp_path),
+                                                prefix="clip", pipeline_path=str(tmp_path / "missing.sav"),
+                                                generateGT=False, vis=False, config=SimpleNamespace())
+        want = bvh_np.poses_to_euler(poses.astype(np.float64), smoothing=False)
+    got = np.load(tmp_path / "clip" / "clip_generated_euler.npy")
+    assert out_poses is poses and got.shape == (24, 45)
+    assert np.abs((got - want + 180.0) % 360.0 - 180.0).max() < 1e-8
