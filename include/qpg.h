@@ -4,8 +4,9 @@
  *
  * The reference (YoungSeng/QPGesture @ 7dd5daa) is pure Python and has no FFI;
  * its boundary for this path is the Python call surface of
- *   codebook/Speech2GestureMatching/GestureKNN.py  (CodeKNN, wavvq_distances)
+ *   codebook/Speech2GestureMatching/GestureKNN.py  (CodeKNN, wavvq_distances; the legacy GestureKNN class)
  *   codebook/models/{vqvae,bottleneck,encdec,resnet}.py (VQVAE encode/decode)
+ *   codebook/PAE.py (Model.forward, pose2phase)  and  process/process_bvh.py (make_bvh_GENEA2020_BT, numeric half)
  * Each entry point below names the reference lines it replaces.  The Python
  * shims in qpgesture_b200/ keep those names/arguments and call this library
  * through ctypes; INTEGRATION.md shows the stub a reference maintainer adds.
