@@ -226,6 +226,9 @@ __global__ void __launch_bounds__(512)
   // searches are independent chains of ~9 dependent gather batches each, so they run side by side
   const int x = tid >> 8, lt = tid & 255;
   const int last = blockIdx.y * 256 + lt;
+  s_inv[0][tid] = 0;                            // ranks are a permutation of 0..511 when they come from this library;
+  s_inv[1][tid] = 0;                            // anything else must still index inside the tables
+  __syncthreads();
   {
     const int c = tid;                          // 512 threads stage one code each
     const int fr = freq_rank[c];
